@@ -1,0 +1,166 @@
+/*
+ * dynrf_b200.h -- C ABI of libdynrf_b200.so: the B200 (sm_100a) ray-march hot path of
+ * RoDynRF's static + dynamic TensoRF fields.
+ *
+ * The reference (facebookresearch/robust-dynrf) has no FFI: its boundary is Python call
+ * signatures.  Each entry point below replaces the ATen kernel
+ * chain behind one reference function; the file:line it replaces is cited per function.
+ * The host-side mirror of those Python signatures lives in robust-dynrf_b200/models and
+ * robust-dynrf_b200/renderer.py and binds this library with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated; fp32 unless stated; masks are uint8.
+ *   - the library allocates nothing persistent, never synchronises the device, never
+ *     throws, never exits.  All work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - return value: 0 = OK; >0 = cudaError_t from the launch; <0 = DYNRF_E_* argument error.
+ *   - planes are channel-LAST: plane i is [H][W][C] for the reference parameter of shape
+ *     (1,C,H,W) (i.e. torch.channels_last strides); line i is [L][C] for (1,C,L,1).
+ *     matMode = {{0,1},{0,2},{1,2}}, vecMode = {2,1,0} (models/tensorBase.py:326-327):
+ *     plane i has W = G[matMode[i][0]], H = G[matMode[i][1]]; line i has L = G[vecMode[i]].
+ *   - MLP layers are "packed": wt is [Kpad][Npad] (input-major, zero padded) built by
+ *     dynrf_pack_linear from nn.Linear's [N][K] weight; bias is [Npad] (zeros if none).
+ */
+#ifndef DYNRF_B200_H
+#define DYNRF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DYNRF_ABI_VERSION 1
+
+#define DYNRF_E_ARG (-1)         /* null pointer / non-positive size */
+#define DYNRF_E_UNSUPPORTED (-2) /* configuration outside the compiled kernels (component counts, widths) */
+#define DYNRF_E_ALIGN (-3)       /* pointer not 16-byte aligned where vector loads need it */
+
+#define DYNRF_RAY_NDC 0
+#define DYNRF_RAY_CONTRACT 1
+
+#define DYNRF_ACT_RELU 0
+#define DYNRF_ACT_SOFTPLUS 1
+
+#define DYNRF_HEAD_FEA 0            /* MLPRender_Fea               models/tensorBase.py:81-111  */
+#define DYNRF_HEAD_FEA_TIMEEMB 1    /* MLPRender_Fea_TimeEmbedding models/tensorBase.py:114-145 */
+#define DYNRF_HEAD_FEA_LATE_VIEW 2  /* MLPRender_Fea_late_view     models/tensorBase.py:148-183 */
+
+/* One vector-matrix decomposed quantity (density, blending or appearance). */
+typedef struct {
+  const float* plane[3]; /* [H][W][C] */
+  const float* line[3];  /* [L][C]    */
+  int32_t C[3], H[3], W[3], L[3];
+} dynrf_vm_t;
+
+/* Gradient buffers with the layout of dynrf_vm_t (accumulated into with atomics; caller zeroes). */
+typedef struct {
+  float* plane[3];
+  float* line[3];
+} dynrf_vm_grad_t;
+
+/* A packed nn.Linear. */
+typedef struct {
+  const float* wt;   /* [Kpad][Npad] */
+  const float* bias; /* [Npad]       */
+  int32_t K, N, Kpad, Npad;
+} dynrf_layer_t;
+
+/* Per-field constants (TensorBase.__init__, models/tensorBase.py:282-339). */
+typedef struct {
+  float aabb_min[3], aabb_max[3];
+  float near_, far_;
+  float distance_scale;   /* 25 in every config */
+  float weight_thres;     /* rayMarch_weight_thres, 1e-4 */
+  float density_shift;    /* softplus only */
+  int32_t act;            /* DYNRF_ACT_* (feature2density, models/tensorBase.py:678-682) */
+  int32_t ray_type;       /* DYNRF_RAY_* */
+} dynrf_field_cfg_t;
+
+int dynrf_abi_version(void);
+/* Human-readable name for a return code (static storage). */
+const char* dynrf_strerror(int code);
+
+/* ---- weight packing ------------------------------------------------------------------
+ * nn.Linear weight [N][K] (+ optional bias [N]) -> wt [Kpad][Npad], bias [Npad].
+ * Kpad = round_up(K,4), Npad = round_up(N,16) are the caller's (see dynrf_pad_k/_n). */
+int dynrf_pad_k(int K);
+int dynrf_pad_n(int N);
+int dynrf_pack_linear(const float* w, const float* bias_or_null, int N, int K, float* wt, float* bias_out, void* stream);
+/* inverse for gradients: dwt [Kpad][Npad] -> dw [N][K] (overwrite) */
+int dynrf_unpack_linear_grad(const float* dwt, int N, int K, float* dw, void* stream);
+
+/* ---- a1-a3: sample generation (renderer.py:147-170; models/tensorBase.py:487-499, 524-559)
+ * zvec[S] is the batch-wide depth vector (one per call, shared by all rays, as in the reference).
+ * jitter pointers are [S] (ndc), [Sin+1] / [Sout+1] (contract) uniforms or NULL for is_train=False. */
+int dynrf_zvec_ndc(float near_, float far_, int S, const float* jitter, float* zvec, void* stream);
+int dynrf_zvec_contract(float near_, float far_, int S, const float* jitter_inner, const float* jitter_outer,
+                        float* zvec, void* stream);
+/* rays [N][6] -> xyz [N][S][3], z_vals [N][S], valid [N][S] (uint8). */
+int dynrf_sample_points(const dynrf_field_cfg_t* cfg, const float* rays, int N, int S, const float* zvec,
+                        float* xyz, float* z_vals, uint8_t* valid, void* stream);
+
+/* ---- a6+a8+a9(+a5): static density lookup + sigma->alpha + transmittance scan -----------
+ * (TensorVMSplit.compute_densityfeature models/tensoRF.py:118-154; feature2density; raw2alpha
+ *  models/tensorBase.py:22-34; the sigma/weight part of TensorBase.forward :717-774).
+ * If xyz == NULL the samples are generated in-kernel from rays + zvec (nothing [N][S][3] is read).
+ * If xyz != NULL then z_vals and valid must be given too ([N][S]).
+ * Outputs: sigma, weight, dists (= delta * |d| * distance_scale) all [N][S];
+ *          active_idx [N*S] int32 + active_count [1] int32 (caller zeroes the counter): flat
+ *          indices n*S+s of samples with weight > weight_thres (the reference's app_mask);
+ *          rgb_zero [N][S][3] or NULL: written 0 for samples NOT in the active list. */
+int dynrf_static_sigma_weight_fwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density, const float* rays, int N, int S,
+                                  const float* xyz, const float* z_vals, const uint8_t* valid, const float* zvec,
+                                  float* sigma, float* weight, float* dists, int32_t* active_idx, int32_t* active_count,
+                                  float* rgb_zero, void* stream);
+
+/* sigma -> weight for a field whose sigma is already known (dynamic field): same outputs as above. */
+int dynrf_alpha_weight_fwd(const dynrf_field_cfg_t* cfg, const float* rays, int N, int S, const float* sigma,
+                           const float* z_vals, float* weight, float* dists, int32_t* active_idx,
+                           int32_t* active_count, float* rgb_zero, void* stream);
+
+/* ---- a7+a11+a12/a13: static appearance for the active samples -----------------------------
+ * (compute_appfeature models/tensoRF.py:156-196 + basis_mat; heads models/tensorBase.py:81-145).
+ * layers: basis (72->27), l1 (138|135 ->128), l2 (128->128), l3 (128|131 -> 3).  rgb [N][S][3]. */
+int dynrf_static_app_fwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* app, const dynrf_layer_t* basis,
+                         const dynrf_layer_t* l1, const dynrf_layer_t* l2, const dynrf_layer_t* l3, int head_mode,
+                         const float* rays, const float* xyz, int N, int S, const int32_t* active_idx,
+                         const int32_t* active_count, float* rgb, void* stream);
+
+/* ---- a15: time embedding + coordinate warp (models/tensoRF.py:521-541) ---------------------
+ * tfeat [N][48]: cols 0..16 = [t, PE(t,8)], cols 17..46 = layer2(relu(layer1(.))), col 47 = 0. */
+int dynrf_time_embed_fwd(const float* ts, int N, const dynrf_layer_t* layer1, const dynrf_layer_t* layer2, float* tfeat,
+                         void* stream);
+/* xyz [P][3] (P = N*S samples of N rays, S per ray) -> xyz_prime [P][3] = unnorm(norm(xyz)) + delta. */
+int dynrf_warp_fwd(const dynrf_field_cfg_t* cfg, const float* xyz, int N, int S, const float* tfeat,
+                   const dynrf_layer_t* layer3, const dynrf_layer_t* layer4, const dynrf_layer_t* layer5,
+                   float* xyz_prime, void* stream);
+
+/* ---- a16+a17: dynamic density + blending (models/tensoRF.py:543-732) ----------------------
+ * 3-scale lookups at normalize(xyz_prime), 152->64->1 MLPs; sigma = act(.), blending = sigmoid(.)
+ * where valid, 0 elsewhere. */
+int dynrf_dyn_sigma_blend_fwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density, const dynrf_vm_t* blending,
+                              const dynrf_layer_t* d1, const dynrf_layer_t* d2, const dynrf_layer_t* b1,
+                              const dynrf_layer_t* b2, const float* xyz, const float* xyz_prime, const uint8_t* valid,
+                              const float* tfeat, int N, int S, float* sigma, float* blend, void* stream);
+
+/* ---- a18+a14: dynamic appearance for the active samples (models/tensoRF.py:734-811;
+ *      MLPRender_Fea_late_view models/tensorBase.py:148-183). */
+int dynrf_dyn_app_fwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* app, const dynrf_layer_t* basis,
+                      const dynrf_layer_t* l1, const dynrf_layer_t* l2, const dynrf_layer_t* l3, const float* rays,
+                      const float* xyz, const float* xyz_prime, const float* tfeat, int N, int S,
+                      const int32_t* active_idx, const int32_t* active_count, float* rgb, void* stream);
+
+/* ---- a19: two-field compositing (renderer.raw2outputs, renderer.py:173-315) ----------------
+ * white_bg: the reference's host-side coin (is_train && rand<0.5), decided by the caller.
+ * out_ray [N][16]: rgb_full3, depth_full, acc_full, rgb_s3, depth_s, acc_s, rgb_d3, depth_d, acc_d, dynamicness.
+ * w_full, w_s, w_d [N][S]. */
+#define DYNRF_RAY_OUT 16
+int dynrf_composite_fwd(int ray_type, int white_bg, const float* rgb_s, const float* sigma_s, const float* rgb_d,
+                        const float* sigma_d, const float* dists, const float* blending, const float* z_vals,
+                        const float* rays, int N, int S, float* out_ray, float* w_full, float* w_s, float* w_d,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNRF_B200_H */

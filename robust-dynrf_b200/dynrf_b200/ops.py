@@ -1,0 +1,256 @@
+"""Torch-facing wrappers around the C ABI: allocate outputs with torch, pass raw device
+pointers + the current CUDA stream to libdynrf_b200.so.  PyTorch is plumbing here (memory,
+streams, autograd bookkeeping); every FLOP of the hot path runs in the library.
+
+Reference functions replaced (paths relative to the reference checkout):
+  sample_xyz            renderer.py:147-170, models/tensorBase.py:487-499,524-559
+  static_field_forward  models/tensorBase.py:704-825 + models/tensoRF.py:118-196
+  dynamic_field_forward models/tensorBase.py:704-850 + models/tensoRF.py:521-811
+  composite             renderer.py:173-315
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as L
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "dynrf_b200: the ray-march hot path runs only on a CUDA device (sm_100a); got a "
+                f"{t.device} tensor. There is no CPU fallback.")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------- parameter layout
+
+
+def to_channel_last_(p: torch.Tensor) -> None:
+    """Make a (1,C,H,W) / (1,C,L,1) parameter physically [H][W][C] while keeping its logical shape
+    (state_dict shape, Adam state and checkpoints are unaffected -- SURVEY.md 7, hard part 1)."""
+    _, c, h, w = p.shape
+    want = (c * h * w, 1, w * c, c)
+    s = p.stride()
+    ok = (c == 1 or s[1] == 1) and (h == 1 or s[2] == want[2]) and (w == 1 or s[3] == want[3])
+    if not ok:
+        with torch.no_grad():
+            p.data = p.data.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+
+
+def vm_struct(planes: Sequence[torch.Tensor], lines: Sequence[torch.Tensor]) -> L.VmT:
+    vm = L.VmT()
+    for i in range(3):
+        to_channel_last_(planes[i])
+        to_channel_last_(lines[i])
+        _, c, h, w = planes[i].shape
+        vm.plane[i] = planes[i].data_ptr()
+        vm.line[i] = lines[i].data_ptr()
+        vm.C[i], vm.H[i], vm.W[i] = c, h, w
+        vm.L[i] = lines[i].shape[2]
+        if lines[i].shape[1] != c:
+            raise ValueError("plane/line component counts differ")
+    return vm
+
+
+def vm_grad_struct(gplanes: Sequence[torch.Tensor], glines: Sequence[torch.Tensor]) -> L.VmGradT:
+    g = L.VmGradT()
+    for i in range(3):
+        g.plane[i] = gplanes[i].data_ptr()
+        g.line[i] = glines[i].data_ptr()
+    return g
+
+
+def zeros_like_cl(p: torch.Tensor) -> torch.Tensor:
+    """zeros with the same (channel-last) strides as parameter p."""
+    return torch.zeros_like(p, memory_format=torch.preserve_format)
+
+
+class PackedLayer:
+    """nn.Linear weight packed to the library's [Kpad][Npad] input-major layout; repacked when the
+    parameter's version counter moves (optimizer steps are in-place)."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor]):
+        self.weight, self.bias = weight, bias
+        lib = L.load()
+        self.N, self.K = weight.shape
+        self.Kpad, self.Npad = lib.dynrf_pad_k(self.K), lib.dynrf_pad_n(self.N)
+        self.wt = torch.empty(self.Kpad * self.Npad, device=weight.device, dtype=torch.float32)
+        self.b = torch.empty(self.Npad, device=weight.device, dtype=torch.float32)
+        self._key = None
+        self.struct = L.LayerT(self.wt.data_ptr(), self.b.data_ptr(), self.K, self.N, self.Kpad, self.Npad)
+
+    def refresh(self) -> L.LayerT:
+        key = (self.weight.data_ptr(), self.weight._version, None if self.bias is None else self.bias._version)
+        if key != self._key:
+            w = _f32c(self.weight.detach())
+            b = None if self.bias is None else _f32c(self.bias.detach())
+            L.check(L.load().dynrf_pack_linear(_p(w), _p(b), self.N, self.K, _p(self.wt), _p(self.b), _stream()),
+                    "dynrf_pack_linear")
+            self._key = key
+        return self.struct
+
+
+def field_cfg(aabb: torch.Tensor, near_far, distance_scale, weight_thres, act: str, density_shift, ray_type: str) -> L.FieldCfgT:
+    a = aabb.detach().cpu().tolist()
+    cfg = L.FieldCfgT()
+    for i in range(3):
+        cfg.aabb_min[i] = a[0][i]
+        cfg.aabb_max[i] = a[1][i]
+    cfg.near_, cfg.far_ = float(near_far[0]), float(near_far[1])
+    cfg.distance_scale = float(distance_scale)
+    cfg.weight_thres = float(weight_thres)
+    cfg.density_shift = float(density_shift)
+    cfg.act = {"relu": L.ACT_RELU, "softplus": L.ACT_SOFTPLUS}[act]
+    cfg.ray_type = {"ndc": L.RAY_NDC, "contract": L.RAY_CONTRACT}[ray_type]
+    return cfg
+
+
+# ----------------------------------------------------------------------------- a1-a3 sampling
+
+
+def make_zvec(cfg: L.FieldCfgT, n_samples: int, ray_type: str, is_train: bool, device) -> torch.Tensor:
+    lib = L.load()
+    zvec = torch.empty(n_samples, device=device, dtype=torch.float32)
+    if ray_type == "ndc":
+        jit = torch.rand(n_samples, device=device) if is_train else None  # one draw shared by all rays
+        L.check(lib.dynrf_zvec_ndc(cfg.near_, cfg.far_, n_samples, _p(jit), _p(zvec), _stream()), "dynrf_zvec_ndc")
+    elif ray_type == "contract":
+        n_in, n_out = n_samples - n_samples // 2, n_samples // 2
+        ji = torch.rand(n_in + 1, device=device) if is_train else None
+        jo = torch.rand(n_out + 1, device=device) if is_train else None
+        L.check(lib.dynrf_zvec_contract(cfg.near_, cfg.far_, n_samples, _p(ji), _p(jo), _p(zvec), _stream()),
+                "dynrf_zvec_contract")
+    else:
+        raise NotImplementedError(
+            "ray_type must be 'ndc' or 'contract' (sample_ray, models/tensorBase.py:501-522, is unused by every config)")
+    return zvec
+
+
+def sample_points(cfg: L.FieldCfgT, rays: torch.Tensor, zvec: torch.Tensor):
+    _require_cuda(rays)
+    rays = _f32c(rays)
+    n, s = rays.shape[0], zvec.shape[0]
+    xyz = torch.empty(n, s, 3, device=rays.device, dtype=torch.float32)
+    z = torch.empty(n, s, device=rays.device, dtype=torch.float32)
+    valid = torch.empty(n, s, device=rays.device, dtype=torch.bool)
+    L.check(L.load().dynrf_sample_points(C.byref(cfg), _p(rays), n, s, _p(zvec), _p(xyz), _p(z), _p(valid), _stream()),
+            "dynrf_sample_points")
+    return xyz, z, valid
+
+
+# ----------------------------------------------------------------------------- field forwards (no autograd)
+
+
+def _active_buffers(n, s, device):
+    idx = torch.empty(n * s, device=device, dtype=torch.int32)
+    cnt = torch.zeros(1, device=device, dtype=torch.int32)
+    return idx, cnt
+
+
+def static_forward_raw(m, rays, xyz, z_vals, valid, ray_type, zvec=None):
+    """-> dict(sigma, weight, dists, rgb, idx, cnt).  xyz=None generates the samples in-kernel from zvec."""
+    lib = L.load()
+    _require_cuda(rays)
+    rays = _f32c(rays)
+    n = rays.shape[0]
+    s = zvec.shape[0] if xyz is None else xyz.shape[1]
+    cfg = m.native_cfg(ray_type)
+    dev = rays.device
+    sigma = torch.empty(n, s, device=dev)
+    weight = torch.empty(n, s, device=dev)
+    dists = torch.empty(n, s, device=dev)
+    rgb = torch.empty(n, s, 3, device=dev)
+    idx, cnt = _active_buffers(n, s, dev)
+    vden = vm_struct(m.density_plane, m.density_line)
+    if xyz is not None:
+        xyz, z_vals = _f32c(xyz), _f32c(z_vals)
+        valid_u8 = valid.contiguous().view(torch.uint8)
+    else:
+        valid_u8 = None
+    L.check(lib.dynrf_static_sigma_weight_fwd(C.byref(cfg), C.byref(vden), _p(rays), n, s, _p(xyz), _p(z_vals), _p(valid_u8),
+                                              _p(zvec), _p(sigma), _p(weight), _p(dists), _p(idx), _p(cnt), _p(rgb), _stream()),
+            "dynrf_static_sigma_weight_fwd")
+    return dict(sigma=sigma, weight=weight, dists=dists, rgb=rgb, idx=idx, cnt=cnt, rays=rays, xyz=xyz, z_vals=z_vals,
+                valid=valid_u8)
+
+
+def static_app_raw(m, st, ray_type):
+    lib = L.load()
+    cfg = m.native_cfg(ray_type)
+    n, s = st["sigma"].shape
+    vapp = vm_struct(m.app_plane, m.app_line)
+    ly = m.packed_layers()
+    L.check(lib.dynrf_static_app_fwd(C.byref(cfg), C.byref(vapp), C.byref(ly["basis"]), C.byref(ly["h1"]), C.byref(ly["h2"]),
+                                     C.byref(ly["h3"]), m.head_mode, _p(st["rays"]), _p(st["xyz"]), n, s, _p(st["idx"]),
+                                     _p(st["cnt"]), _p(st["rgb"]), _stream()),
+            "dynrf_static_app_fwd")
+
+
+def dynamic_forward_raw(m, rays, ts, xyz, z_vals, valid, ray_type):
+    lib = L.load()
+    _require_cuda(rays, ts, xyz)
+    rays, ts, xyz, z_vals = _f32c(rays), _f32c(ts), _f32c(xyz), _f32c(z_vals)
+    valid_u8 = valid.contiguous().view(torch.uint8)
+    n, s = z_vals.shape
+    dev = rays.device
+    cfg = m.native_cfg(ray_type)
+    ly = m.packed_layers()
+    tfeat = torch.empty(n, L.TFEAT, device=dev)
+    L.check(lib.dynrf_time_embed_fwd(_p(ts), n, C.byref(ly["layer1"]), C.byref(ly["layer2"]), _p(tfeat), _stream()),
+            "dynrf_time_embed_fwd")
+    xyz_prime = torch.empty(n, s, 3, device=dev)
+    L.check(lib.dynrf_warp_fwd(C.byref(cfg), _p(xyz), n, s, _p(tfeat), C.byref(ly["layer3"]), C.byref(ly["layer4"]),
+                               C.byref(ly["layer5"]), _p(xyz_prime), _stream()), "dynrf_warp_fwd")
+    sigma = torch.empty(n, s, device=dev)
+    blend = torch.empty(n, s, device=dev)
+    vden = vm_struct(m.density_plane, m.density_line)
+    vbl = vm_struct(m.blending_plane, m.blending_line)
+    L.check(lib.dynrf_dyn_sigma_blend_fwd(C.byref(cfg), C.byref(vden), C.byref(vbl), C.byref(ly["d1"]), C.byref(ly["d2"]),
+                                          C.byref(ly["b1"]), C.byref(ly["b2"]), _p(xyz), _p(xyz_prime), _p(valid_u8), _p(tfeat),
+                                          n, s, _p(sigma), _p(blend), _stream()), "dynrf_dyn_sigma_blend_fwd")
+    weight = torch.empty(n, s, device=dev)
+    dists = torch.empty(n, s, device=dev)
+    rgb = torch.empty(n, s, 3, device=dev)
+    idx, cnt = _active_buffers(n, s, dev)
+    L.check(lib.dynrf_alpha_weight_fwd(C.byref(cfg), _p(rays), n, s, _p(sigma), _p(z_vals), _p(weight), _p(dists), _p(idx),
+                                       _p(cnt), _p(rgb), _stream()), "dynrf_alpha_weight_fwd")
+    vapp = vm_struct(m.app_plane, m.app_line)
+    L.check(lib.dynrf_dyn_app_fwd(C.byref(cfg), C.byref(vapp), C.byref(ly["basis"]), C.byref(ly["h1"]), C.byref(ly["h2"]),
+                                  C.byref(ly["h3"]), _p(rays), _p(xyz), _p(xyz_prime), _p(tfeat), n, s, _p(idx), _p(cnt),
+                                  _p(rgb), _stream()), "dynrf_dyn_app_fwd")
+    return dict(sigma=sigma, blend=blend, weight=weight, dists=dists, rgb=rgb, xyz_prime=xyz_prime, tfeat=tfeat, idx=idx,
+                cnt=cnt, rays=rays, ts=ts, xyz=xyz, z_vals=z_vals, valid=valid_u8)
+
+
+def composite_raw(rgb_s, sigma_s, rgb_d, sigma_d, dists, blending, z_vals, rays, white_bg: bool, ray_type: str):
+    lib = L.load()
+    _require_cuda(rgb_s, sigma_s, rgb_d, sigma_d, dists, blending, z_vals, rays)
+    args = [_f32c(t) for t in (rgb_s, sigma_s, rgb_d, sigma_d, dists, blending, z_vals, rays)]
+    n, s = args[1].shape
+    dev = args[1].device
+    out_ray = torch.empty(n, L.RAY_OUT, device=dev)
+    w_full = torch.empty(n, s, device=dev)
+    w_s = torch.empty(n, s, device=dev)
+    w_d = torch.empty(n, s, device=dev)
+    rt = {"ndc": L.RAY_NDC, "contract": L.RAY_CONTRACT}.get(ray_type, 2)
+    L.check(lib.dynrf_composite_fwd(rt, int(bool(white_bg)), *[_p(a) for a in args], n, s, _p(out_ray), _p(w_full), _p(w_s),
+                                    _p(w_d), _stream()), "dynrf_composite_fwd")
+    return out_ray, w_full, w_s, w_d, args

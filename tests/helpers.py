@@ -1,0 +1,142 @@
+"""Shared by tests/, __graft_entry__.smoke() and bench.py: build the same seeded model pair for the
+CPU oracle and the native drop-in modules, run one evaluation pass through each, compare."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "robust-dynrf_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from oracle import rodynrf_oracle as O  # noqa: E402
+
+NDC_AABB = [[-1.5, -1.67, -1.0], [1.5, 1.67, 1.0]]  # dataLoader/nvidia.py:246-251
+CONTRACT_AABB = [[-2.0, -2.0, -2.0], [2.0, 2.0, 2.0]]
+
+COMMON = dict(density_n_comp=[16, 4, 4], appearance_n_comp=[48, 12, 12], app_dim=27, alphaMask_thres=1e-4,
+              density_shift=-10, distance_scale=25, pos_pe=6, view_pe=0, featureC=128, step_ratio=2.0, fea2denseAct="relu")
+
+
+def synth_rays(n, ray_type, gen, spread=0.1):
+    """SURVEY.md 8d value distributions."""
+    if ray_type == "ndc":
+        o = torch.cat((torch.rand(n, 2, generator=gen) * 2 - 1, -torch.ones(n, 1)), -1)
+        d = torch.cat((spread * torch.randn(n, 2, generator=gen), 2 * torch.ones(n, 1)), -1)
+    else:
+        o = 0.05 * torch.randn(n, 3, generator=gen)
+        d = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=-1)
+    ts = torch.rand(n, generator=gen) * 2 - 1
+    return torch.cat((o, d), -1), ts
+
+
+def build_pair(grid, n_rays, n_samples, ray_type="ndc", static_mode="MLP_Fea", seed=0, sd_static=None, sd_dynamic=None,
+               rays=None, ts=None, aabb=None, near_far=None):
+    gen = torch.Generator().manual_seed(seed)
+    if aabb is None:
+        aabb = torch.tensor(NDC_AABB if ray_type == "ndc" else CONTRACT_AABB)
+    if near_far is None:
+        near_far = (0.0, 1.0) if ray_type == "ndc" else (0.0, 256.0)
+    cs = O.FieldCfg(aabb=aabb, near_far=tuple(near_far), shadingMode=static_mode, fea_pe=2, dynamic=False)
+    cd = O.FieldCfg(aabb=aabb, near_far=tuple(near_far), shadingMode="MLP_Fea_late_view", fea_pe=0, dynamic=True)
+    if sd_static is None:
+        sd_static = O.init_state_dict(cs, grid, gen)
+        sd_dynamic = O.init_state_dict(cd, grid, gen)
+    if rays is None:
+        rays, ts = synth_rays(n_rays, ray_type, gen)
+    return dict(grid=list(grid), aabb=aabb, near_far=tuple(near_far), ray_type=ray_type, static_mode=static_mode, cs=cs,
+                cd=cd, sd_static=sd_static, sd_dynamic=sd_dynamic, rays=rays, ts=ts, n_samples=n_samples)
+
+
+def native_models(case, device):
+    import models.tensoRF as T
+
+    dev = torch.device(device)
+    aabb = case["aabb"].to(dev)
+    kw = dict(COMMON, near_far=list(case["near_far"]))
+    static = T.TensorVMSplit(aabb, case["grid"], 12, dev, shadingMode=case["static_mode"], fea_pe=2, **kw)
+    dyn = T.TensorVMSplit_TimeEmbedding(aabb, case["grid"], 12, dev, shadingMode="MLP_Fea_late_view", fea_pe=0, **kw)
+    static.load_state_dict(case["sd_static"])
+    missing = dyn.load_state_dict(case["sd_dynamic"], strict=False)
+    assert not missing.unexpected_keys and all(k.startswith("scene_flow") for k in missing.missing_keys), missing
+    return static, dyn
+
+
+def oracle_pass(case, xyz=None, z=None, valid=None):
+    with torch.no_grad():
+        if xyz is None:
+            xyz, z, valid = O.sampleXYZ(case["cd"], case["rays"], case["n_samples"], case["ray_type"], False)
+        fs = O.field_forward(case["cs"], case["sd_static"], case["rays"], case["ts"], xyz, z, valid, case["ray_type"])
+        fd = O.field_forward(case["cd"], case["sd_dynamic"], case["rays"], case["ts"], xyz, z, valid, case["ray_type"])
+        out = O.raw2outputs(fs[6], fs[7], fd[6], fd[7], fd[9], fd[2], fd[8], case["rays"], False, case["ray_type"])
+    return dict(xyz=xyz, z=z, valid=valid, fs=fs, fd=fd, out=out)
+
+
+def native_pass(case, device="cuda:0", models=None):
+    import renderer as R
+
+    static, dyn = models if models is not None else native_models(case, device)
+    rays, ts = case["rays"].to(device), case["ts"].to(device)
+    with torch.no_grad():
+        xyz, z, valid = R.sampleXYZ(dyn, rays, case["n_samples"], case["ray_type"], False)
+        fs = static(rays, ts, None, xyz, z, valid, is_train=False, ray_type=case["ray_type"], N_samples=case["n_samples"])
+        fd = dyn(rays, ts, None, xyz, z, valid, is_train=False, ray_type=case["ray_type"], N_samples=case["n_samples"])
+        out = R.raw2outputs(fs[6], fs[7], fd[6], fd[7], fd[9], fd[2], fd[8], rays, False, case["ray_type"])
+    torch.cuda.synchronize()
+    cpu = lambda t: None if t is None else t.detach().cpu()  # noqa: E731
+    return dict(xyz=cpu(xyz), z=cpu(z), valid=cpu(valid), fs=tuple(cpu(t) for t in fs), fd=tuple(cpu(t) for t in fd),
+                out=tuple(cpu(t) for t in out))
+
+
+# tolerances (BASELINE.json north_star): alpha within 1e-5, composited RGB within 1e-4 relative
+TOL_ALPHA = 1e-5
+TOL_RGB_REL = 1e-4
+
+
+def _maxabs(a, b):
+    return float((a - b).abs().max()) if a.numel() else 0.0
+
+
+def compare_pass(ref, got, thres=1e-4, check=True):
+    """Returns a dict of max errors; asserts the north-star tolerances when check=True."""
+    rep = {}
+    rep["xyz"] = _maxabs(ref["xyz"], got["xyz"])
+    rep["z"] = _maxabs(ref["z"], got["z"])
+    rep["valid_mismatch"] = int((ref["valid"] != got["valid"]).sum())
+    for tag, key in (("s", "fs"), ("d", "fd")):
+        r, g = ref[key], got[key]
+        dists = r[9]
+        a_ref = 1 - torch.exp(-r[7] * dists)
+        a_got = 1 - torch.exp(-g[7] * g[9])
+        rep[f"{tag}_alpha"] = _maxabs(a_ref, a_got)
+        rep[f"{tag}_sigma"] = _maxabs(r[7], g[7])
+        rep[f"{tag}_weight"] = _maxabs(r[4], g[4])
+        rep[f"{tag}_dists"] = _maxabs(r[9], g[9])
+        # per-sample rgb where the app mask is unambiguous (|w - thres| > 1e-6) in both
+        clear = ((r[4] - thres).abs() > 1e-6)
+        rep[f"{tag}_rgb"] = _maxabs(r[6][clear], g[6][clear])
+        rep[f"{tag}_mask_flips"] = int(((r[4] > thres) != (g[4] > thres)).sum())
+    rep["d_blending"] = _maxabs(ref["fd"][2], got["fd"][2])
+    rep["d_xyz_prime"] = _maxabs(ref["fd"][5], got["fd"][5])
+    names = ["rgb_full", "depth_full", "acc_full", "w_full", "rgb_s", "depth_s", "acc_s", "w_s", "rgb_d", "depth_d", "acc_d",
+             "w_d", "dyn"]
+    for i, nme in enumerate(names):
+        r, g = ref["out"][i], got["out"][i]
+        rep[f"o_{nme}"] = _maxabs(r, g)
+        if nme.startswith("rgb"):
+            rep[f"o_{nme}_rel"] = float(((r - g).abs() / r.abs().clamp_min(1e-2)).max())
+    if check:
+        assert rep["valid_mismatch"] == 0, rep
+        assert rep["xyz"] <= 1e-6 and rep["z"] <= 1e-6, rep
+        assert rep["s_alpha"] <= TOL_ALPHA and rep["d_alpha"] <= TOL_ALPHA, rep
+        assert rep["s_weight"] <= 2e-5 and rep["d_weight"] <= 2e-5, rep
+        assert rep["d_blending"] <= 2e-5, rep
+        assert rep["d_xyz_prime"] <= 2e-5, rep
+        assert rep["s_rgb"] <= 1e-4 and rep["d_rgb"] <= 1e-4, rep
+        for k in ("rgb_full", "rgb_s", "rgb_d"):
+            assert rep[f"o_{k}_rel"] <= TOL_RGB_REL + 1e-4 * (rep["s_mask_flips"] + rep["d_mask_flips"] > 0), rep
+        for k in ("acc_full", "acc_s", "acc_d", "w_full", "w_s", "w_d", "dyn"):
+            assert rep[f"o_{k}"] <= 5e-5, rep
+    return rep
