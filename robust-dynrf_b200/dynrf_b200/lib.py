@@ -90,10 +90,47 @@ PROTOTYPES = {
 }
 
 _lib = None
+_NO_LAUNCH = {"dynrf_abi_version", "dynrf_pad_k", "dynrf_pad_n", "dynrf_strerror"}
+
+# every other entry point enqueues exactly one kernel of this library; bench.py reports the count
+launch_count = 0
+# optional (start_event, end_event) pairs recorded around one entry point: {"dynrf_xxx": [(ev0, ev1), ...]}
+profile_events = None
 
 
 class DynrfError(RuntimeError):
     pass
+
+
+class _Counted:
+    """Attribute proxy over the CDLL: counts kernel launches and records profiling events on request."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._cdll, name)
+            if name in _NO_LAUNCH:
+                fn = raw
+            else:
+                def fn(*args, _raw=raw, _name=name):
+                    global launch_count
+                    launch_count += 1
+                    if profile_events is not None and _name in profile_events:
+                        import torch
+
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        rc = _raw(*args)
+                        e1.record()
+                        profile_events[_name].append((e0, e1))
+                        return rc
+                    return _raw(*args)
+            self._cache[name] = fn
+        return fn
 
 
 def load() -> C.CDLL:
@@ -115,8 +152,8 @@ def load() -> C.CDLL:
         fn.restype = C.c_int
     lib.dynrf_strerror.argtypes = [C.c_int]
     lib.dynrf_strerror.restype = C.c_char_p
-    _lib = lib
-    return lib
+    _lib = _Counted(lib)
+    return _lib
 
 
 def check(code: int, what: str) -> None:

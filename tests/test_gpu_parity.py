@@ -129,5 +129,6 @@ def test_octree_render_signature():
     assert len(out) == 11 and out[0] is None and out[6] is None
     torch.testing.assert_close(out[2], full[2])
     torch.testing.assert_close(out[5], full[5] - xyz)
-    out_s = R.OctreeRender_trilinear_fast(rays, ts, None, static, xyz, z, valid, chunk=32, N_samples=16, device=DEV)
+    with torch.no_grad():
+        out_s = R.OctreeRender_trilinear_fast(rays, ts, None, static, xyz, z, valid, chunk=32, N_samples=16, device=DEV)
     assert out_s[2] is None and out_s[5] is None and out_s[8].shape == (50, 16)
