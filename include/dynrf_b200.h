@@ -65,6 +65,12 @@ typedef struct {
   int32_t K, N, Kpad, Npad;
 } dynrf_layer_t;
 
+/* Gradient of a packed nn.Linear (same [Kpad][Npad] / [Npad] layout; accumulated into, caller zeroes). */
+typedef struct {
+  float* dwt;
+  float* dbias;
+} dynrf_layer_grad_t;
+
 /* Per-field constants (TensorBase.__init__, models/tensorBase.py:282-339). */
 typedef struct {
   float aabb_min[3], aabb_max[3];
@@ -159,6 +165,70 @@ int dynrf_composite_fwd(int ray_type, int white_bg, const float* rgb_s, const fl
                         const float* sigma_d, const float* dists, const float* blending, const float* z_vals,
                         const float* rays, int N, int S, float* out_ray, float* w_full, float* w_s, float* w_d,
                         void* stream);
+
+/* ======================================================================================
+ * Backward entry points (what autograd through grid_sampler_2d_backward / addmm / cumprod computes in
+ * the reference; SURVEY.md 7 hard part 2).  All gradient outputs are ACCUMULATED into unless stated.
+ * ====================================================================================== */
+
+/* nn.Linear weight [N][K] -> wb [nrows_pad][Jpad], wb[n][j] = w[n][k0+j] (Jpad = round_up(k1-k0,16)): the operand of
+ * the data-gradient GEMM dX = dY x W restricted to input columns k0..k1. */
+int dynrf_pack_linear_bwd(const float* w, int N, int K, int k0, int k1, int nrows_pad, float* wb, void* stream);
+
+/* weight = alpha*T backward (models/tensorBase.py:22-34): gsigma += , gdists += . */
+int dynrf_alpha_weight_bwd(int N, int S, const float* sigma, const float* dists, const float* gweight, float* gsigma,
+                           float* gdists, void* stream);
+
+/* renderer.raw2outputs backward.  g_out_ray [N][16]; g_w_* [N][S] or NULL.  Outputs are OVERWRITTEN:
+ * g_rgb_s/g_rgb_d [N][S][3], g_sigma_s/g_sigma_d/g_dists/g_blend [N][S], g_rays [N][6]. */
+int dynrf_composite_bwd(int ray_type, int white_bg, const float* rgb_s, const float* sigma_s, const float* rgb_d,
+                        const float* sigma_d, const float* dists, const float* blending, const float* z_vals,
+                        const float* rays, int N, int S, const float* g_out_ray, const float* g_w_full, const float* g_w_s,
+                        const float* g_w_d, float* g_rgb_s, float* g_sigma_s, float* g_rgb_d, float* g_sigma_d,
+                        float* g_dists, float* g_blend, float* g_rays, void* stream);
+
+/* static density lookup backward (grid_sampler_2d_backward of models/tensoRF.py:118-154): gsigma [N][S] is
+ * d loss / d sigma; gxyz [N][S][3] (+=) may be NULL. */
+int dynrf_static_density_bwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density, const dynrf_vm_grad_t* gdensity,
+                             const float* xyz, const uint8_t* valid, const float* sigma, const float* gsigma, int N, int S,
+                             float* gxyz, void* stream);
+
+/* static appearance backward.  wb2 = pack_bwd(l2.w,0,128,128 rows); wb1 = pack_bwd(l1.w,0,K,128 rows);
+ * wbB = pack_bwd(basis.w,0,72,32 rows).  grgb [N][S][3].  gxyz (+=) and gviewdir [N][3] (+=) may be NULL. */
+int dynrf_static_app_bwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* app, const dynrf_vm_grad_t* gapp,
+                         const dynrf_layer_t* basis, const dynrf_layer_t* l1, const dynrf_layer_t* l2, const dynrf_layer_t* l3,
+                         int head_mode, const float* wb2, const float* wb1, const float* wbB, const float* rays,
+                         const float* xyz, int N, int S, const int32_t* active_idx, const int32_t* active_count,
+                         const float* grgb, const dynrf_layer_grad_t* gB, const dynrf_layer_grad_t* g1,
+                         const dynrf_layer_grad_t* g2, const dynrf_layer_grad_t* g3, float* gxyz, float* gviewdir, void* stream);
+
+/* dynamic appearance backward.  wb1f = pack_bwd(l1.w,0,27,128 rows); wbB = 3 x pack_bwd(basis.w, 72 si, 72 si+72, 32 rows)
+ * concatenated.  gxp [N][S][3] += d loss / d xyz_prime. */
+int dynrf_dyn_app_bwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* app, const dynrf_vm_grad_t* gapp,
+                      const dynrf_layer_t* basis, const dynrf_layer_t* l1, const dynrf_layer_t* l2, const dynrf_layer_t* l3,
+                      const float* wb2, const float* wb1f, const float* wbB, const float* rays, const float* xyz,
+                      const float* xyz_prime, const float* tfeat, int N, int S, const int32_t* active_idx,
+                      const int32_t* active_count, const float* grgb, const dynrf_layer_grad_t* gB,
+                      const dynrf_layer_grad_t* g1, const dynrf_layer_grad_t* g2, const dynrf_layer_grad_t* g3, float* gxp,
+                      void* stream);
+
+/* dynamic density (mode 0) / blending (mode 1) MLP + lookup backward.  wb1f = pack_bwd(l1.w,0,72,64 rows).
+ * gout [N][S] = d loss / d sigma | d blending.  gxp [N][S][3] += . */
+int dynrf_dyn_mlp_bwd(const dynrf_field_cfg_t* cfg, int mode, const dynrf_vm_t* vm, const dynrf_vm_grad_t* gvm,
+                      const dynrf_layer_t* l1, const dynrf_layer_t* l2, const float* wb1f, const float* xyz,
+                      const float* xyz_prime, const uint8_t* valid, const float* tfeat, int N, int S, const float* gout,
+                      const dynrf_layer_grad_t* g1, const dynrf_layer_grad_t* g2, float* gxp, void* stream);
+
+/* coordinate warp backward.  wb4 = pack_bwd(layer4.w,0,64,64 rows); wb3t = pack_bwd(layer3.w,63,93,64 rows).
+ * gxp [N][S][3] = total d loss / d xyz_prime.  gtout [N][32] += d loss / d t_out (per ray). */
+int dynrf_warp_bwd(const dynrf_field_cfg_t* cfg, const float* xyz, int N, int S, const float* tfeat, const dynrf_layer_t* l3,
+                   const dynrf_layer_t* l4, const dynrf_layer_t* l5, const float* wb4, const float* wb3t, const float* gxp,
+                   const dynrf_layer_grad_t* g3, const dynrf_layer_grad_t* g4, const dynrf_layer_grad_t* g5, float* gtout,
+                   void* stream);
+
+/* time-embedding MLP backward: gtout [N][32] -> packed gradients of layer1 / layer2. */
+int dynrf_time_embed_bwd(const float* ts, int N, const dynrf_layer_t* l1, const dynrf_layer_t* l2, const float* gtout,
+                         const dynrf_layer_grad_t* g1, const dynrf_layer_grad_t* g2, void* stream);
 
 #ifdef __cplusplus
 }

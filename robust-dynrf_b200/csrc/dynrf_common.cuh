@@ -51,6 +51,9 @@ __device__ __forceinline__ float unnorm_coord(float xn, float mn, float inv) {
 struct Tap1 {
   int i0, i1;     // texel indices in the FULL-resolution axis (already multiplied by stride); valid only if w != 0
   float w0, w1;   // weights, 0 when the tap is out of range
+  float r0, r1;   // raw weights (1 - frac, frac) regardless of range      (backward)
+  float scale;    // d(index)/d(coord) = (n_s - 1) / 2                      (backward)
+  bool v0, v1;    // tap in range                                           (backward)
 };
 
 __device__ __forceinline__ Tap1 make_tap(float x, int n, int s) {
@@ -58,9 +61,11 @@ __device__ __forceinline__ Tap1 make_tap(float x, int n, int s) {
   // grid_sampler_unnormalize(align_corners=True): ((x + 1) / 2) * (size - 1)
   const float f = __fmul_rn(__fmul_rn(__fadd_rn(x, 1.0f), 0.5f), (float)(ns - 1));
   Tap1 t;
+  t.scale = 0.5f * (float)(ns - 1);
   if (!(f > -1.0f && f < (float)ns)) {  // also catches NaN
     t.i0 = t.i1 = 0;
-    t.w0 = t.w1 = 0.f;
+    t.w0 = t.w1 = t.r0 = t.r1 = 0.f;
+    t.v0 = t.v1 = false;
     return t;
   }
   const float fl = floorf(f);
@@ -73,6 +78,10 @@ __device__ __forceinline__ Tap1 make_tap(float x, int n, int s) {
   t.i1 = v1 ? (i0 + 1) * s : 0;
   t.w0 = v0 ? w0 : 0.f;
   t.w1 = v1 ? w1 : 0.f;
+  t.r0 = w0;
+  t.r1 = w1;
+  t.v0 = v0;
+  t.v1 = v1;
   return t;
 }
 

@@ -5,7 +5,7 @@
 // All of them push tiles of 128 samples through the tile MLP engine (dynrf_mlp.cuh):
 // gather / encode the layer input feature-major into shared memory, run the dense layers,
 // apply the narrow output layer per sample.  Grids are persistent (a multiple of the SM count).
-#include "dynrf_mlp.cuh"
+#include "dynrf_tile.cuh"
 
 namespace dynrf {
 
@@ -64,71 +64,13 @@ __global__ void __launch_bounds__(64) k_time_embed(const float* __restrict__ ts,
   if (j == 47) o[47] = 0.f;
 }
 
-// ------------------------------------------------------------------------------------------------
-// shared tile scratch
-
-struct TileScratch {
-  float xn[3][kTileM];   // normalize(xyz)                       (un-warped, "xyz_sampled" of the feature fns)
-  float xq[3][kTileM];   // second coordinate set (kernel specific: xn2 / normalize(xyz_prime))
-  float xu[3][kTileM];   // unnormalize(xn) (warp kernel)
-  int ray[kTileM];       // ray index of the sample, -1 = padding row
-  int idx[kTileM];       // flat sample index
-  int on[kTileM];        // sample takes part in gathers (valid / active)
-};
-
-// rows [row_base .. row_base + sumC) of A <- plane*line products at coordinate set xq, stride s.
-__device__ __forceinline__ void gather_vm_rows(const dynrf_vm_t& vm, const float (*xq)[kTileM], int stride, int row_base,
-                                               float* __restrict__ A, int tid, const int* __restrict__ on) {
-  const int m = tid & (kTileM - 1), part = tid >> 7;
-  const bool act = on[m] != 0;
-  const float x3[3] = {xq[0][m], xq[1][m], xq[2][m]};
-  int q = 0, coff = 0;
-#pragma unroll
-  for (int pl = 0; pl < 3; ++pl) {
-    const int C = vm.C[pl], ng = C >> 2;
-    int u, v, l;
-    plane_axes(pl, u, v, l);
-    Tap1 tu, tv, tl;
-    if (act) {
-      tu = make_tap(x3[u], vm.W[pl], stride);
-      tv = make_tap(x3[v], vm.H[pl], stride);
-      tl = make_tap(x3[l], vm.L[pl], stride);
-    }
-    for (int g = ((q & 1) == part) ? 0 : 1; g < ng; g += 2) {
-      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (act) r = vm_group(vm.plane[pl], vm.line[pl], C, vm.W[pl], tu, tv, tl, g * 4);
-      float* a = A + (size_t)(row_base + coff + g * 4) * kTileM + m;
-      a[0] = r.x;
-      a[kTileM] = r.y;
-      a[2 * kTileM] = r.z;
-      a[3 * kTileM] = r.w;
-    }
-    q += ng;
-    coff += C;
-  }
-}
-
-// rows [r0, r0+80) <- [xn(3), sin PE(xn,10) (30), cos (30), t, sin PE(t,8), cos PE(t,8)]  (needs scr.xn, scr.ray)
-__device__ __forceinline__ void fill_pos_time_rows(const TileScratch& scr, const float* __restrict__ tfeat, float* __restrict__ A,
-                                                   int r0, int tid) {
-  for (int item = tid; item < 3 * kTileM; item += kMlpThreads) {
-    const int m = item & (kTileM - 1), d = item >> 7;
-    const float x = scr.xn[d][m];
-    A[(size_t)(r0 + d) * kTileM + m] = x;
-    pe_rows<10>(x, A, r0 + 3 + d * 10, r0 + 33 + d * 10, m);
-  }
-  for (int item = tid; item < 17 * kTileM; item += kMlpThreads) {
-    const int m = item & (kTileM - 1), k = item >> 7;
-    const int ry = scr.ray[m];
-    A[(size_t)(r0 + 63 + k) * kTileM + m] = ry >= 0 ? __ldg(tfeat + (size_t)ry * kTFeat + k) : 0.f;
-  }
-}
+using Scratch = TileScratch<kTileM>;
 
 // ------------------------------------------------------------------------------------------------
 // a15 (space branch): xyz -> xyz_prime.   smem: A[96][128] | H1[64][128] | wbuf | scratch ; H2 aliases A
 
 constexpr int kWarpK = 96;  // 93 padded
-constexpr size_t kWarpSmem = (size_t)(kWarpK * kTileM + 64 * kTileM + 2 * kChunkK * 64) * sizeof(float) + sizeof(TileScratch);
+constexpr size_t kWarpSmem = (size_t)(kWarpK * kTileM + 64 * kTileM + 2 * kChunkK * 64) * sizeof(float) + sizeof(Scratch);
 
 __global__ void __launch_bounds__(kMlpThreads)
 k_warp(dynrf_field_cfg_t cfg, const float* __restrict__ xyz, int P, int S, const float* __restrict__ tfeat, dynrf_layer_t l3,
@@ -137,7 +79,7 @@ k_warp(dynrf_field_cfg_t cfg, const float* __restrict__ xyz, int P, int S, const
   float* A = smem;
   float* H1 = A + kWarpK * kTileM;
   float* wbuf = H1 + 64 * kTileM;
-  TileScratch& scr = *reinterpret_cast<TileScratch*>(wbuf + 2 * kChunkK * 64);
+  Scratch& scr = *reinterpret_cast<Scratch*>(wbuf + 2 * kChunkK * 64);
   float* H2 = A;
   const int tid = threadIdx.x;
   const AabbNorm nb = make_norm(cfg);
@@ -158,24 +100,13 @@ k_warp(dynrf_field_cfg_t cfg, const float* __restrict__ xyz, int P, int S, const
       }
     }
     __syncthreads();
-    // rows 0..2 xn2 | 3..32 sin | 33..62 cos | 63..92 t_out | 93..95 zero
-    for (int item = tid; item < 3 * kTileM; item += kMlpThreads) {
-      const int m = item & (kTileM - 1), d = item >> 7;
-      const float x = scr.xq[d][m];
-      A[(size_t)d * kTileM + m] = x;
-      pe_rows<10>(x, A, 3 + d * 10, 33 + d * 10, m);
-    }
-    for (int item = tid; item < 33 * kTileM; item += kMlpThreads) {
-      const int m = item & (kTileM - 1), k = item >> 7;
-      const int ry = scr.ray[m];
-      A[(size_t)(63 + k) * kTileM + m] = (k < 30 && ry >= 0) ? __ldg(tfeat + (size_t)ry * kTFeat + 17 + k) : 0.f;
-    }
+    fill_warp_rows<kTileM, kTileM>(scr, tfeat, A, tid);
     __syncthreads();
-    dense_tile<64, true>(A, l3, H1, wbuf, tid);
-    dense_tile<64, true>(H1, l4, H2, wbuf, tid);
+    dense_tile<64, kTileM, kTileM, true>(A, l3, H1, wbuf, tid);
+    dense_tile<64, kTileM, kTileM, true>(H1, l4, H2, wbuf, tid);
     if (tid < kTileM) {
       float d3[3];
-      small_dense<3>(H2, 64, l5, tid, d3);
+      small_dense<3, kTileM>(H2, 64, l5, tid, d3);
       const int i = tile * kTileM + tid;
       if (i < P) {
 #pragma unroll
@@ -191,7 +122,7 @@ k_warp(dynrf_field_cfg_t cfg, const float* __restrict__ xyz, int P, int S, const
 // smem: A[152][128] | H[64][128] | wbuf[2][32][64] | scratch
 
 constexpr int kSbK = 152;
-constexpr size_t kSbSmem = (size_t)(kSbK * kTileM + 64 * kTileM + 2 * kChunkK * 64) * sizeof(float) + sizeof(TileScratch);
+constexpr size_t kSbSmem = (size_t)(kSbK * kTileM + 64 * kTileM + 2 * kChunkK * 64) * sizeof(float) + sizeof(Scratch);
 
 __global__ void __launch_bounds__(kMlpThreads)
 k_dyn_sigma_blend(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_layer_t d1, dynrf_layer_t d2, dynrf_layer_t b1,
@@ -202,7 +133,7 @@ k_dyn_sigma_blend(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_
   float* A = smem;
   float* H = A + kSbK * kTileM;
   float* wbuf = H + 64 * kTileM;
-  TileScratch& scr = *reinterpret_cast<TileScratch*>(wbuf + 2 * kChunkK * 64);
+  Scratch& scr = *reinterpret_cast<Scratch*>(wbuf + 2 * kChunkK * 64);
   const int tid = threadIdx.x;
   const AabbNorm nb = make_norm(cfg);
   const int ntiles = (P + kTileM - 1) / kTileM;
@@ -221,17 +152,17 @@ k_dyn_sigma_blend(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_
       }
     }
     __syncthreads();
-    fill_pos_time_rows(scr, tfeat, A, 72, tid);
+    fill_pos_time_rows<kTileM, kTileM>(scr, tfeat, A, 72, tid);
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       const dynrf_vm_t& vm = which == 0 ? vden : vbl;
 #pragma unroll 1
-      for (int si = 0; si < 3; ++si) gather_vm_rows(vm, scr.xq, 1 << si, si * 24, A, tid, scr.on);
+      for (int si = 0; si < 3; ++si) gather_vm_rows<kTileM, kTileM>(vm, scr.xq, 1 << si, si * 24, A, tid, scr.on);
       __syncthreads();
-      dense_tile<64, true>(A, which == 0 ? d1 : b1, H, wbuf, tid);
+      dense_tile<64, kTileM, kTileM, true>(A, which == 0 ? d1 : b1, H, wbuf, tid);
       if (tid < kTileM) {
         float o[1];
-        small_dense<1>(H, 64, which == 0 ? d2 : b2, tid, o);
+        small_dense<1, kTileM>(H, 64, which == 0 ? d2 : b2, tid, o);
         const int i = tile * kTileM + tid;
         if (i < P) {
           const bool v = scr.on[tid] != 0;
@@ -252,7 +183,7 @@ k_dyn_sigma_blend(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_
 // X rows: 0..26 app feature | 27..29 xn | 30..59 sin | 60..89 cos | 90 t | 91..98 sin t | 99..106 cos t | 107 zero
 
 constexpr int kDaK = 108;
-constexpr size_t kDaSmem = (size_t)(72 * kTileM + kDaK * kTileM + 128 * kTileM + 2 * kChunkK * 128) * sizeof(float) + sizeof(TileScratch);
+constexpr size_t kDaSmem = (size_t)(72 * kTileM + kDaK * kTileM + 128 * kTileM + 2 * kChunkK * 128) * sizeof(float) + sizeof(Scratch);
 
 __global__ void __launch_bounds__(kMlpThreads)
 k_dyn_app(dynrf_field_cfg_t cfg, dynrf_vm_t vapp, dynrf_layer_t basis, dynrf_layer_t l1, dynrf_layer_t l2, dynrf_layer_t l3,
@@ -264,7 +195,7 @@ k_dyn_app(dynrf_field_cfg_t cfg, dynrf_vm_t vapp, dynrf_layer_t basis, dynrf_lay
   float* X = Ac + 72 * kTileM;
   float* H1 = X + kDaK * kTileM;
   float* wbuf = H1 + 128 * kTileM;
-  TileScratch& scr = *reinterpret_cast<TileScratch*>(wbuf + 2 * kChunkK * 128);
+  Scratch& scr = *reinterpret_cast<Scratch*>(wbuf + 2 * kChunkK * 128);
   float* H2 = Ac;
   const int tid = threadIdx.x;
   const AabbNorm nb = make_norm(cfg);
@@ -287,29 +218,27 @@ k_dyn_app(dynrf_field_cfg_t cfg, dynrf_vm_t vapp, dynrf_layer_t basis, dynrf_lay
       }
     }
     __syncthreads();
-    fill_pos_time_rows(scr, tfeat, X, 27, tid);
+    fill_pos_time_rows<kTileM, kTileM>(scr, tfeat, X, 27, tid);
     if (tid < kTileM) X[(size_t)107 * kTileM + tid] = 0.f;
     // basis_mat over the 3 strides: 216 -> 27, accumulated 72 rows at a time
-    Acc<32> fa;
-    acc_init<32>(fa, nullptr, tid >> 4);
+    Acc<32, kTileM> fa;
+    acc_init<32, kTileM>(fa, nullptr, tid >> 4);
 #pragma unroll 1
     for (int si = 0; si < 3; ++si) {
-      gather_vm_rows(vapp, scr.xq, 1 << si, 0, Ac, tid, scr.on);
+      gather_vm_rows<kTileM, kTileM>(vapp, scr.xq, 1 << si, 0, Ac, tid, scr.on);
       __syncthreads();
-      acc_gemm<32>(fa, Ac, 72, basis.wt + (size_t)si * 72 * 32, wbuf, tid);
+      acc_gemm<32, kTileM, kTileM>(fa, Ac, 72, basis.wt + (size_t)si * 72 * 32, wbuf, tid);
     }
-    acc_store<32, false>(fa, X, 27, tid);
-    dense_tile<128, true>(X, l1, H1, wbuf, tid);
-    dense_tile<128, true>(H1, l2, H2, wbuf, tid);
+    acc_store<32, kTileM, kTileM, false>(fa, X, 27, tid);
+    dense_tile<128, kTileM, kTileM, true>(X, l1, H1, wbuf, tid);
+    dense_tile<128, kTileM, kTileM, true>(H1, l2, H2, wbuf, tid);
     if (tid < kTileM) {
       float o[3];
-      small_dense<3>(H2, 128, l3, tid, o);
+      small_dense<3, kTileM>(H2, 128, l3, tid, o);
       if (scr.on[tid]) {
         // mlp_view input = [h(128), viewdir(3)], viewdir = d / |d|  (models/tensorBase.py:723-725,174-180)
-        const int ry = scr.ray[tid];
-        const float dx = __ldg(rays + (size_t)ry * 6 + 3), dy = __ldg(rays + (size_t)ry * 6 + 4), dz = __ldg(rays + (size_t)ry * 6 + 5);
-        const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-        const float vd[3] = {__fdiv_rn(dx, nrm), __fdiv_rn(dy, nrm), __fdiv_rn(dz, nrm)};
+        float vd[3];
+        ray_viewdir(rays, scr.ray[tid], vd);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           float v = o[c];
@@ -330,7 +259,7 @@ k_dyn_app(dynrf_field_cfg_t cfg, dynrf_vm_t vapp, dynrf_layer_t basis, dynrf_lay
 // MLP_Fea_TimeEmb   X rows: 0..26 feat | 27..80 sin PE(feat,2) | 81..134 cos | 135 zero ; viewdir enters the last layer
 
 constexpr int kSaK = 140;
-constexpr size_t kSaSmem = (size_t)(72 * kTileM + kSaK * kTileM + 128 * kTileM + 2 * kChunkK * 128) * sizeof(float) + sizeof(TileScratch);
+constexpr size_t kSaSmem = (size_t)(72 * kTileM + kSaK * kTileM + 128 * kTileM + 2 * kChunkK * 128) * sizeof(float) + sizeof(Scratch);
 
 template <int HEAD>
 __global__ void __launch_bounds__(kMlpThreads)
@@ -342,7 +271,7 @@ k_static_app(dynrf_field_cfg_t cfg, dynrf_vm_t vapp, dynrf_layer_t basis, dynrf_
   float* X = Ac + 72 * kTileM;
   float* H1 = X + kSaK * kTileM;
   float* wbuf = H1 + 128 * kTileM;
-  TileScratch& scr = *reinterpret_cast<TileScratch*>(wbuf + 2 * kChunkK * 128);
+  Scratch& scr = *reinterpret_cast<Scratch*>(wbuf + 2 * kChunkK * 128);
   float* H2 = Ac;
   const int tid = threadIdx.x;
   const AabbNorm nb = make_norm(cfg);
@@ -359,14 +288,7 @@ k_static_app(dynrf_field_cfg_t cfg, dynrf_vm_t vapp, dynrf_layer_t basis, dynrf_
       scr.ray[tid] = in ? i / S : -1;
       scr.on[tid] = in ? 1 : 0;
       float vd[3] = {0.f, 0.f, 0.f};
-      if (in) {
-        const int ry = i / S;
-        const float dx = __ldg(rays + (size_t)ry * 6 + 3), dy = __ldg(rays + (size_t)ry * 6 + 4), dz = __ldg(rays + (size_t)ry * 6 + 5);
-        const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-        vd[0] = __fdiv_rn(dx, nrm);
-        vd[1] = __fdiv_rn(dy, nrm);
-        vd[2] = __fdiv_rn(dz, nrm);
-      }
+      if (in) ray_viewdir(rays, i / S, vd);
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         const float x = in ? __ldg(xyz + (size_t)i * 3 + a) : 0.f;
@@ -383,23 +305,23 @@ k_static_app(dynrf_field_cfg_t cfg, dynrf_vm_t vapp, dynrf_layer_t basis, dynrf_
       }
     }
     __syncthreads();
-    gather_vm_rows(vapp, scr.xq, 1, 0, Ac, tid, scr.on);
+    gather_vm_rows<kTileM, kTileM>(vapp, scr.xq, 1, 0, Ac, tid, scr.on);
     __syncthreads();
-    Acc<32> fa;
-    acc_init<32>(fa, nullptr, tid >> 4);
-    acc_gemm<32>(fa, Ac, 72, basis.wt, wbuf, tid);
-    acc_store<32, false>(fa, X, 27, tid);
+    Acc<32, kTileM> fa;
+    acc_init<32, kTileM>(fa, nullptr, tid >> 4);
+    acc_gemm<32, kTileM, kTileM>(fa, Ac, 72, basis.wt, wbuf, tid);
+    acc_store<32, kTileM, kTileM, false>(fa, X, 27, tid);
     // PE(feat, 2): dim-major, freq-minor (models/tensorBase.py:13-19)
     for (int item = tid; item < 27 * kTileM; item += kMlpThreads) {
       const int m = item & (kTileM - 1), d = item >> 7;
-      pe_rows<2>(X[(size_t)d * kTileM + m], X, kSin0 + d * 2, kCos0 + d * 2, m);
+      pe_rows<2, kTileM>(X[(size_t)d * kTileM + m], X, kSin0 + d * 2, kCos0 + d * 2, m);
     }
     __syncthreads();
-    dense_tile<128, true>(X, l1, H1, wbuf, tid);
-    dense_tile<128, true>(H1, l2, H2, wbuf, tid);
+    dense_tile<128, kTileM, kTileM, true>(X, l1, H1, wbuf, tid);
+    dense_tile<128, kTileM, kTileM, true>(H1, l2, H2, wbuf, tid);
     if (tid < kTileM) {
       float o[3];
-      small_dense<3>(H2, 128, l3, tid, o);
+      small_dense<3, kTileM>(H2, 128, l3, tid, o);
       if (scr.on[tid]) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -417,17 +339,6 @@ k_static_app(dynrf_field_cfg_t cfg, dynrf_vm_t vapp, dynrf_layer_t basis, dynrf_
 }
 
 // ------------------------------------------------------------------------------------------------
-
-static int g_sm_count = 0;
-static int sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0, n = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    g_sm_count = n > 0 ? n : 148;
-  }
-  return g_sm_count;
-}
 
 }  // namespace dynrf
 

@@ -1,0 +1,336 @@
+"""torch.autograd.Function wrappers over the *_bwd entry points of libdynrf_b200.so.
+
+Gradient coverage (SURVEY.md 8a "autograd requirements per pass"):
+  * every parameter of both fields (planes, lines, basis, heads, warp / density / blending MLPs, time MLP);
+  * static field: d/dxyz (-> rays, poses, focal; PASS 5-9), d/dviewdir, d/ddists;
+  * compositing: every tensor input and the NDC background term of `rays`;
+  * dynamic field: d/ddists only.  Gradients of the dynamic outputs w.r.t. xyz / view direction are not
+    produced: in the reference train loop they only ever reach the loss multiplied by zero (only the *_s
+    outputs of the passes that feed rays with grad are used, train.py:1812,2216,2281) and
+    MLPRender_Fea_late_view detaches the view direction.
+Small per-ray glue (norm / normalisation chain rule on [N,3] tensors) is done with torch ops inside backward.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import lib as L
+from . import ops
+from .ops import _p, _stream, _f32c
+
+
+def available() -> bool:
+    try:
+        lib = L.load()
+        return hasattr(lib, "dynrf_dyn_mlp_bwd")
+    except Exception:
+        return False
+
+
+class GradLayer:
+    """Packed gradient buffers of one nn.Linear."""
+
+    def __init__(self, pl: ops.PackedLayer):
+        self.pl = pl
+        self.dwt = torch.zeros(pl.Kpad * pl.Npad, device=pl.wt.device)
+        self.db = torch.zeros(pl.Npad, device=pl.wt.device)
+        self.struct = L.LayerGradT(self.dwt.data_ptr(), self.db.data_ptr())
+
+    def unpack(self):
+        dw = torch.empty(self.pl.N, self.pl.K, device=self.dwt.device)
+        L.check(L.load().dynrf_unpack_linear_grad(_p(self.dwt), self.pl.N, self.pl.K, _p(dw), _stream()), "unpack_linear_grad")
+        return dw, (self.db[: self.pl.N].clone() if self.pl.bias is not None else None)
+
+
+def pack_bwd(pl: ops.PackedLayer, k0: int, k1: int, nrows: int) -> torch.Tensor:
+    """wb[n][j] = W[n][k0+j]; cached on the PackedLayer per parameter version."""
+    cache = pl.__dict__.setdefault("_bwd_cache", {})
+    key = (k0, k1, nrows)
+    ver = (pl.weight.data_ptr(), pl.weight._version)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    jpad = (k1 - k0 + 15) // 16 * 16
+    wb = torch.empty(nrows * jpad, device=pl.wt.device)
+    w = _f32c(pl.weight.detach())
+    L.check(L.load().dynrf_pack_linear_bwd(_p(w), pl.N, pl.K, k0, k1, nrows, _p(wb), _stream()), "dynrf_pack_linear_bwd")
+    cache[key] = (ver, wb)
+    return wb
+
+
+def _vm_grads(planes, lines):
+    gp = [ops.zeros_like_cl(p) for p in planes]
+    gl = [ops.zeros_like_cl(p) for p in lines]
+    return gp, gl, ops.vm_grad_struct(gp, gl)
+
+
+def _rays_grad_from(rays, z_vals, scale, gdists, gvd):
+    """Chain rule of dists = dz*|d|*scale and viewdir = d/|d| back to rays[:, 3:6]."""
+    d = rays[:, 3:6]
+    nrm = d.norm(dim=-1, keepdim=True)
+    v = d / nrm
+    g = torch.zeros_like(rays)
+    if gdists is not None:
+        dz = torch.cat((z_vals[:, 1:] - z_vals[:, :-1], torch.zeros_like(z_vals[:, :1])), -1)
+        gn = (gdists * dz).sum(-1, keepdim=True) * scale
+        g[:, 3:6] += gn * v
+    if gvd is not None:
+        g[:, 3:6] += (gvd - (gvd * v).sum(-1, keepdim=True) * v) / nrm
+    return g
+
+
+# ----------------------------------------------------------------------------- sampling
+
+
+class SamplePointsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rays, zvec, model, ray_type):
+        cfg = model.native_cfg(ray_type)
+        xyz, z, valid = ops.sample_points(cfg, rays.detach(), zvec)
+        ctx.save_for_backward(rays.detach(), zvec)
+        ctx.ray_type = ray_type
+        ctx.mark_non_differentiable(z, valid)
+        return xyz, z, valid
+
+    @staticmethod
+    def backward(ctx, gxyz, _gz, _gv):
+        rays, zvec = ctx.saved_tensors
+        if ctx.ray_type == "ndc":
+            g = torch.cat((gxyz.sum(1), (gxyz * zvec[None, :, None]).sum(1)), -1)
+            return g, None, None, None
+        # contraction Jacobian (models/tensorBase.py:552-556): recompute the tiny formula under autograd
+        with torch.enable_grad():
+            r = rays.clone().requires_grad_(True)
+            p = r[:, None, :3] + r[:, None, 3:6] * zvec[None, :, None]
+            linf = p.abs().amax(-1, keepdim=True)
+            pc = torch.where(linf > 1.0, (2 - 1 / linf) * (p / linf), p)
+            (g,) = torch.autograd.grad(pc, r, gxyz)
+        return g, None, None, None
+
+
+# ----------------------------------------------------------------------------- fields
+
+
+def _static_params(m):
+    rm = m.renderModule
+    last = rm.mlp_view[0] if rm.split_view else rm.mlp[4]
+    return (list(m.density_plane) + list(m.density_line) + list(m.app_plane) + list(m.app_line)
+            + [m.basis_mat.weight, rm.mlp[0].weight, rm.mlp[0].bias, rm.mlp[2].weight, rm.mlp[2].bias, last.weight, last.bias])
+
+
+class StaticFieldFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, ray_type, rays, xyz, z_vals, valid, *params):
+        st = ops.static_forward_raw(model, rays.detach(), xyz.detach(), z_vals.detach(), valid, ray_type)
+        ops.static_app_raw(model, st, ray_type)
+        ctx.model, ctx.ray_type, ctx.st = model, ray_type, st
+        ctx.set_materialize_grads(False)
+        return st["sigma"], st["weight"], st["rgb"], st["dists"]
+
+    @staticmethod
+    def backward(ctx, gsigma, gweight, grgb, gdists):
+        lib = L.load()
+        m, rt, st = ctx.model, ctx.ray_type, ctx.st
+        cfg = m.native_cfg(rt)
+        n, s = st["sigma"].shape
+        dev = st["sigma"].device
+        gsig = _f32c(gsigma).clone() if gsigma is not None else torch.zeros(n, s, device=dev)
+        gd = _f32c(gdists).clone() if gdists is not None else torch.zeros(n, s, device=dev)
+        if gweight is not None:
+            L.check(lib.dynrf_alpha_weight_bwd(n, s, _p(st["sigma"]), _p(st["dists"]), _p(_f32c(gweight)), _p(gsig), _p(gd),
+                                               _stream()), "dynrf_alpha_weight_bwd")
+        need_xyz = ctx.needs_input_grad[3]
+        need_rays = ctx.needs_input_grad[2]
+        gxyz = torch.zeros(n, s, 3, device=dev) if need_xyz else None
+        gvd = torch.zeros(n, 3, device=dev) if need_rays else None
+        ly = m.packed_layers()
+        pk = m._packed
+        gden_p, gden_l, gden = _vm_grads(m.density_plane, m.density_line)
+        gapp_p, gapp_l, gapp = _vm_grads(m.app_plane, m.app_line)
+        gl = {k: GradLayer(pk[k]) for k in ("basis", "h1", "h2", "h3")}
+        if grgb is not None:
+            vapp = ops.vm_struct(m.app_plane, m.app_line)
+            wb2 = pack_bwd(pk["h2"], 0, 128, 128)
+            wb1 = pack_bwd(pk["h1"], 0, pk["h1"].K, 128)
+            wbB = pack_bwd(pk["basis"], 0, 72, 32)
+            L.check(lib.dynrf_static_app_bwd(C.byref(cfg), C.byref(vapp), C.byref(gapp), C.byref(ly["basis"]), C.byref(ly["h1"]),
+                                             C.byref(ly["h2"]), C.byref(ly["h3"]), m.head_mode, _p(wb2), _p(wb1), _p(wbB),
+                                             _p(st["rays"]), _p(st["xyz"]), n, s, _p(st["idx"]), _p(st["cnt"]), _p(_f32c(grgb)),
+                                             C.byref(gl["basis"].struct), C.byref(gl["h1"].struct), C.byref(gl["h2"].struct),
+                                             C.byref(gl["h3"].struct), _p(gxyz), _p(gvd), _stream()), "dynrf_static_app_bwd")
+        vden = ops.vm_struct(m.density_plane, m.density_line)
+        L.check(lib.dynrf_static_density_bwd(C.byref(cfg), C.byref(vden), C.byref(gden), _p(st["xyz"]), _p(st["valid"]),
+                                             _p(st["sigma"]), _p(gsig), n, s, _p(gxyz), _stream()), "dynrf_static_density_bwd")
+        grays = _rays_grad_from(st["rays"], st["z_vals"], float(m.distance_scale), gd, gvd) if need_rays else None
+        gb, _ = gl["basis"].unpack()
+        g1w, g1b = gl["h1"].unpack()
+        g2w, g2b = gl["h2"].unpack()
+        g3w, g3b = gl["h3"].unpack()
+        pg = gden_p + gden_l + gapp_p + gapp_l + [gb, g1w, g1b, g2w, g2b, g3w, g3b]
+        return (None, None, grays, gxyz, None, None, *pg)
+
+
+def _dynamic_params(m):
+    rm = m.renderModule
+    lin = [m.basis_mat, rm.mlp[0], rm.mlp[2], rm.mlp_view[0], m.layer1, m.layer2, m.layer3, m.layer4, m.layer5,
+           m.density_layer1, m.density_layer2, m.blending_layer1, m.blending_layer2]
+    ps = (list(m.blending_plane) + list(m.blending_line) + list(m.density_plane) + list(m.density_line)
+          + list(m.app_plane) + list(m.app_line))
+    for l in lin:
+        ps.append(l.weight)
+        if l.bias is not None:
+            ps.append(l.bias)
+    return ps
+
+
+_DYN_LAYER_ORDER = ["basis", "h1", "h2", "h3", "layer1", "layer2", "layer3", "layer4", "layer5", "d1", "d2", "b1", "b2"]
+
+
+class DynamicFieldFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, ray_type, rays, ts, xyz, z_vals, valid, *params):
+        r = ops.dynamic_forward_raw(model, rays.detach(), ts.detach(), xyz.detach(), z_vals.detach(), valid, ray_type)
+        ctx.model, ctx.ray_type, ctx.r = model, ray_type, r
+        ctx.set_materialize_grads(False)
+        return r["blend"], r["weight"], r["xyz_prime"], r["rgb"], r["sigma"], r["dists"]
+
+    @staticmethod
+    def backward(ctx, gblend, gweight, gxyzp, grgb, gsigma, gdists):
+        lib = L.load()
+        m, rt, r = ctx.model, ctx.ray_type, ctx.r
+        cfg = m.native_cfg(rt)
+        n, s = r["sigma"].shape
+        dev = r["sigma"].device
+        gsig = _f32c(gsigma).clone() if gsigma is not None else torch.zeros(n, s, device=dev)
+        gd = _f32c(gdists).clone() if gdists is not None else torch.zeros(n, s, device=dev)
+        if gweight is not None:
+            L.check(lib.dynrf_alpha_weight_bwd(n, s, _p(r["sigma"]), _p(r["dists"]), _p(_f32c(gweight)), _p(gsig), _p(gd),
+                                               _stream()), "dynrf_alpha_weight_bwd")
+        gxp = _f32c(gxyzp).clone() if gxyzp is not None else torch.zeros(n, s, 3, device=dev)
+        ly = m.packed_layers()
+        pk = m._packed
+        gl = {k: GradLayer(pk[k]) for k in _DYN_LAYER_ORDER}
+        gbl_p, gbl_l, gbl = _vm_grads(m.blending_plane, m.blending_line)
+        gden_p, gden_l, gden = _vm_grads(m.density_plane, m.density_line)
+        gapp_p, gapp_l, gapp = _vm_grads(m.app_plane, m.app_line)
+        if grgb is not None:
+            vapp = ops.vm_struct(m.app_plane, m.app_line)
+            wb2 = pack_bwd(pk["h2"], 0, 128, 128)
+            wb1f = pack_bwd(pk["h1"], 0, 27, 128)
+            wbB = torch.cat([pack_bwd(pk["basis"], 72 * i, 72 * i + 72, 32) for i in range(3)])
+            L.check(lib.dynrf_dyn_app_bwd(C.byref(cfg), C.byref(vapp), C.byref(gapp), C.byref(ly["basis"]), C.byref(ly["h1"]),
+                                          C.byref(ly["h2"]), C.byref(ly["h3"]), _p(wb2), _p(wb1f), _p(wbB), _p(r["rays"]),
+                                          _p(r["xyz"]), _p(r["xyz_prime"]), _p(r["tfeat"]), n, s, _p(r["idx"]), _p(r["cnt"]),
+                                          _p(_f32c(grgb)), C.byref(gl["basis"].struct), C.byref(gl["h1"].struct),
+                                          C.byref(gl["h2"].struct), C.byref(gl["h3"].struct), _p(gxp), _stream()),
+                    "dynrf_dyn_app_bwd")
+        vden = ops.vm_struct(m.density_plane, m.density_line)
+        vbl = ops.vm_struct(m.blending_plane, m.blending_line)
+        for mode, vm, gvm, k1, k2, gout in ((0, vden, gden, "d1", "d2", gsig), (1, vbl, gbl, "b1", "b2", gblend)):
+            if gout is None:
+                continue
+            wbf = pack_bwd(pk[k1], 0, 72, 64)
+            L.check(lib.dynrf_dyn_mlp_bwd(C.byref(cfg), mode, C.byref(vm), C.byref(gvm), C.byref(ly[k1]), C.byref(ly[k2]), _p(wbf),
+                                          _p(r["xyz"]), _p(r["xyz_prime"]), _p(r["valid"]), _p(r["tfeat"]), n, s, _p(_f32c(gout)),
+                                          C.byref(gl[k1].struct), C.byref(gl[k2].struct), _p(gxp), _stream()), "dynrf_dyn_mlp_bwd")
+        gtout = torch.zeros(n, 32, device=dev)
+        wb4 = pack_bwd(pk["layer4"], 0, 64, 64)
+        wb3t = pack_bwd(pk["layer3"], 63, 93, 64)
+        L.check(lib.dynrf_warp_bwd(C.byref(cfg), _p(r["xyz"]), n, s, _p(r["tfeat"]), C.byref(ly["layer3"]), C.byref(ly["layer4"]),
+                                   C.byref(ly["layer5"]), _p(wb4), _p(wb3t), _p(gxp), C.byref(gl["layer3"].struct),
+                                   C.byref(gl["layer4"].struct), C.byref(gl["layer5"].struct), _p(gtout), _stream()),
+                "dynrf_warp_bwd")
+        L.check(lib.dynrf_time_embed_bwd(_p(r["ts"]), n, C.byref(ly["layer1"]), C.byref(ly["layer2"]), _p(gtout),
+                                         C.byref(gl["layer1"].struct), C.byref(gl["layer2"].struct), _stream()),
+                "dynrf_time_embed_bwd")
+        grays = _rays_grad_from(r["rays"], r["z_vals"], float(m.distance_scale), gd, None) if ctx.needs_input_grad[2] else None
+        pg = gbl_p + gbl_l + gden_p + gden_l + gapp_p + gapp_l
+        for k in _DYN_LAYER_ORDER:
+            dw, db = gl[k].unpack()
+            pg.append(dw)
+            if db is not None:
+                pg.append(db)
+        return (None, None, grays, None, None, None, None, *pg)
+
+
+def field_forward_with_grad(model, rays, ts, xyz, z_vals, valid, ray_type):
+    if model.is_dynamic:
+        blend, weight, xyzp, rgb, sigma, dists = DynamicFieldFn.apply(model, ray_type, rays, ts, xyz, z_vals, valid,
+                                                                       *_dynamic_params(model))
+        return None, None, blend, xyz, weight, xyzp, rgb, sigma, z_vals, dists
+    sigma, weight, rgb, dists = StaticFieldFn.apply(model, ray_type, rays, xyz, z_vals, valid, *_static_params(model))
+    return None, None, None, xyz, weight, None, rgb, sigma, z_vals, dists
+
+
+# ----------------------------------------------------------------------------- compositing
+
+
+class CompositeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb_s, sigma_s, rgb_d, sigma_d, dists, blending, z_vals, rays, white, ray_type):
+        o, w_full, w_s, w_d, args = ops.composite_raw(rgb_s.detach(), sigma_s.detach(), rgb_d.detach(), sigma_d.detach(),
+                                                      dists.detach(), blending.detach(), z_vals.detach(), rays.detach(), white,
+                                                      ray_type)
+        ctx.args, ctx.white, ctx.ray_type = args, white, ray_type
+        ctx.set_materialize_grads(False)
+        return o, w_full, w_s, w_d
+
+    @staticmethod
+    def backward(ctx, go, gwf, gws, gwd):
+        lib = L.load()
+        rgb_s, sigma_s, rgb_d, sigma_d, dists, blending, z_vals, rays = ctx.args
+        n, s = sigma_s.shape
+        dev = sigma_s.device
+        go = _f32c(go) if go is not None else torch.zeros(n, L.RAY_OUT, device=dev)
+        g_rgb_s, g_rgb_d = torch.empty(n, s, 3, device=dev), torch.empty(n, s, 3, device=dev)
+        g_ss, g_sd, g_di, g_bl = (torch.empty(n, s, device=dev) for _ in range(4))
+        g_rays = torch.empty(n, 6, device=dev)
+        rt = {"ndc": L.RAY_NDC, "contract": L.RAY_CONTRACT}.get(ctx.ray_type, 2)
+        opt = lambda t: None if t is None else _f32c(t)  # noqa: E731
+        gwf, gws, gwd = opt(gwf), opt(gws), opt(gwd)
+        L.check(lib.dynrf_composite_bwd(rt, int(bool(ctx.white)), _p(rgb_s), _p(sigma_s), _p(rgb_d), _p(sigma_d), _p(dists),
+                                        _p(blending), _p(z_vals), _p(rays), n, s, _p(go), _p(gwf), _p(gws), _p(gwd), _p(g_rgb_s),
+                                        _p(g_ss), _p(g_rgb_d), _p(g_sd), _p(g_di), _p(g_bl), _p(g_rays), _stream()),
+                "dynrf_composite_bwd")
+        if rays.shape[1] != 6:
+            g_rays = None
+        return g_rgb_s, g_ss, g_rgb_d, g_sd, g_di, g_bl, None, g_rays, None, None
+
+
+# ----------------------------------------------------------------------------- the timed train step
+
+
+def train_step(step, rays, ts, target):
+    """fwd + bwd of both fields through the public API, MSE on the three composited colours, Adam update."""
+    import renderer as R
+
+    static, dyn = step.static, step.dyn
+    if getattr(step, "opt", None) is None:
+        params = list(static.parameters()) + [p for n_, p in dyn.named_parameters() if not n_.startswith("scene_flow")]
+        step.params = params
+        step.opt = torch.optim.Adam(params, lr=1e-4, betas=(0.9, 0.99))
+    xyz, z, valid = R.sampleXYZ(dyn, rays, step.s, step.rt, True)
+    fs = static(rays, ts, None, xyz, z, valid, is_train=True, ray_type=step.rt, N_samples=step.s)
+    fd = dyn(rays, ts, None, xyz, z, valid, is_train=True, ray_type=step.rt, N_samples=step.s)
+    o = R.raw2outputs(fs[6], fs[7], fd[6], fd[7], fd[9], fd[2], fd[8], rays, False, step.rt)
+    loss = ((o[0] - target) ** 2).mean() + ((o[4] - target) ** 2).mean() + ((o[8] - target) ** 2).mean()
+    step.opt.zero_grad(set_to_none=True)
+    loss.backward()
+    if step.world > 1:
+        import torch.distributed as dist
+
+        grads = [p.grad for p in step.params if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)
+        flat /= step.world
+        off = 0
+        for g in grads:
+            k = g.numel()
+            g.copy_(flat[off:off + k].view_as(g))
+            off += k
+    step.opt.step()
+    out = torch.cat((o[0], o[1][:, None], o[2][:, None], o[4], o[5][:, None], o[6][:, None], o[8], o[9][:, None],
+                     o[10][:, None], o[12][:, None]), -1).detach()
+    return out

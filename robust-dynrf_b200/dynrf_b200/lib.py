@@ -66,8 +66,13 @@ class FieldCfgT(C.Structure):
                 ("act", C.c_int32), ("ray_type", C.c_int32)]
 
 
+class LayerGradT(C.Structure):
+    _fields_ = [("dwt", C.c_void_p), ("dbias", C.c_void_p)]
+
+
 _P, _I, _F = C.c_void_p, C.c_int, C.c_float
 _cfg, _vm, _ly, _vg = C.POINTER(FieldCfgT), C.POINTER(VmT), C.POINTER(LayerT), C.POINTER(VmGradT)
+_lg = C.POINTER(LayerGradT)
 
 # name -> argtypes; every entry point include/dynrf_b200.h declares (tests check the two lists agree)
 PROTOTYPES = {
@@ -87,6 +92,18 @@ PROTOTYPES = {
     "dynrf_dyn_sigma_blend_fwd": [_cfg, _vm, _vm, _ly, _ly, _ly, _ly, _P, _P, _P, _P, _I, _I, _P, _P, _P],
     "dynrf_dyn_app_fwd": [_cfg, _vm, _ly, _ly, _ly, _ly, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P],
     "dynrf_composite_fwd": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
+    # backward
+    "dynrf_pack_linear_bwd": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "dynrf_alpha_weight_bwd": [_I, _I, _P, _P, _P, _P, _P, _P],
+    "dynrf_composite_bwd": [_I, _I] + [_P] * 8 + [_I, _I] + [_P] * 4 + [_P] * 7 + [_P],
+    "dynrf_static_density_bwd": [_cfg, _vm, _vg, _P, _P, _P, _P, _I, _I, _P, _P],
+    "dynrf_static_app_bwd": [_cfg, _vm, _vg, _ly, _ly, _ly, _ly, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _lg, _lg, _lg,
+                             _lg, _P, _P, _P],
+    "dynrf_dyn_app_bwd": [_cfg, _vm, _vg, _ly, _ly, _ly, _ly, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _lg, _lg, _lg,
+                          _lg, _P, _P],
+    "dynrf_dyn_mlp_bwd": [_cfg, _I, _vm, _vg, _ly, _ly, _P, _P, _P, _P, _P, _I, _I, _P, _lg, _lg, _P, _P],
+    "dynrf_warp_bwd": [_cfg, _P, _I, _I, _P, _ly, _ly, _ly, _P, _P, _P, _lg, _lg, _lg, _P, _P],
+    "dynrf_time_embed_bwd": [_P, _I, _ly, _ly, _P, _lg, _lg, _P],
 }
 
 _lib = None

@@ -1,0 +1,190 @@
+"""GPU gradient parity (-m gpu): backward kernels vs autograd through the CPU oracle (itself pinned
+against autograd through the unmodified reference by tests/test_oracle_golden.py::test_gradients)."""
+import pytest
+import torch
+
+from tests import helpers as H
+from oracle import rodynrf_oracle as O
+
+gpu = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def _grad_ok(a, b, loose=3e-2, l2=5e-3):
+    """Agreement robust to ReLU-kink flips: a hidden unit whose pre-activation is ~1e-7 can land on the other side
+    of 0 on the GPU; that moves the unit's gradient row -- and, more weakly, everything upstream of it -- by one
+    sample's contribution (observed: 4e-3 of max on one row, everything else <= 4e-5).  Criterion: max-norm error
+    <= 3e-2 of max|ref| and L2 error <= 5e-3 of ||ref||; a wrong or missing term fails both by orders of magnitude."""
+    scale = float(b.abs().max()) + 1e-12
+    err = (a - b).abs() / scale
+    rel2 = float((a - b).norm() / (b.norm() + 1e-12))
+    return float(err.max()) <= loose and rel2 <= l2, float(err.max()), rel2
+
+
+def _loss_weights(shapes, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(s, generator=g) for s in shapes]
+
+
+def _oracle_full(case, rays_grad=False):
+    ss = {k: v.clone().requires_grad_(True) for k, v in case["sd_static"].items()}
+    sd = {k: v.clone().requires_grad_(True) for k, v in case["sd_dynamic"].items()}
+    rays = case["rays"].clone().requires_grad_(rays_grad)
+    xyz, z, valid = O.sampleXYZ(case["cd"], rays, case["n_samples"], case["ray_type"], False)
+    fs = O.field_forward(case["cs"], ss, rays, case["ts"], xyz, z, valid, case["ray_type"])
+    fd = O.field_forward(case["cd"], sd, rays, case["ts"], xyz, z, valid, case["ray_type"])
+    o = O.raw2outputs(fs[6], fs[7], fd[6], fd[7], fd[9], fd[2], fd[8], rays, False, case["ray_type"])
+    return ss, sd, rays, fs, fd, o
+
+
+def _native_full(case, rays_grad=False):
+    import renderer as R
+
+    static, dyn = H.native_models(case, DEV)
+    rays = case["rays"].to(DEV).requires_grad_(rays_grad)
+    ts = case["ts"].to(DEV)
+    xyz, z, valid = R.sampleXYZ(dyn, rays, case["n_samples"], case["ray_type"], False)
+    fs = static(rays, ts, None, xyz, z, valid, ray_type=case["ray_type"])
+    fd = dyn(rays, ts, None, xyz, z, valid, ray_type=case["ray_type"])
+    o = R.raw2outputs(fs[6], fs[7], fd[6], fd[7], fd[9], fd[2], fd[8], rays, False, case["ray_type"])
+    return static, dyn, rays, fs, fd, o
+
+
+@gpu
+@pytest.mark.parametrize("ray_type,static_mode,grid,n,s", [
+    ("ndc", "MLP_Fea", [21, 24, 18], 96, 40),
+    ("contract", "MLP_Fea_TimeEmbedding", [16, 19, 20], 70, 33),
+    ("ndc", "MLP_Fea", [40, 44, 36], 200, 150),
+])
+def test_parameter_gradients(ray_type, static_mode, grid, n, s):
+    case = H.build_pair(grid, n, s, ray_type=ray_type, static_mode=static_mode, seed=7 * n + s)
+    ss, sd, _, fs, fd, o = _oracle_full(case)
+    shapes = [t.shape for t in o] + [fd[5].shape, fd[2].shape, fs[4].shape]
+    ws = _loss_weights(shapes, 99)
+    loss = sum((t * w).sum() for t, w in zip(list(o) + [fd[5], fd[2], fs[4]], ws))
+    loss.backward()
+
+    static, dyn, _, fs2, fd2, o2 = _native_full(case)
+    loss2 = sum((t * w.to(DEV)).sum() for t, w in zip(list(o2) + [fd2[5], fd2[2], fs2[4]], ws))
+    loss2.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss2) - float(loss)) <= 1e-4 * max(1.0, abs(float(loss)))
+    worst = {}
+    for tag, mod, sdict in (("s", static, ss), ("d", dyn, sd)):
+        for name, p in mod.named_parameters():
+            if name.startswith("scene_flow"):
+                continue
+            ref = sdict[name].grad
+            assert ref is not None, name
+            assert p.grad is not None, f"{tag}:{name} got no gradient"
+            assert p.grad.shape == ref.shape
+            worst[f"{tag}:{name}"] = _grad_ok(p.grad.cpu(), ref)
+    bad = {k: v for k, v in worst.items() if not v[0]}
+    print(sorted(((k, v[1], v[2]) for k, v in worst.items()), key=lambda kv: -kv[1])[:8])
+    assert not bad, bad
+
+
+@gpu
+@pytest.mark.parametrize("ray_type,static_mode", [("ndc", "MLP_Fea"), ("contract", "MLP_Fea_TimeEmbedding")])
+def test_static_ray_gradients(ray_type, static_mode):
+    """PASS 5 shape: rays carry grad -> xyz -> static field; d loss / d rays (pose / focal chain)."""
+    import renderer as R
+
+    case = H.build_pair([24, 28, 20], 80, 48, ray_type=ray_type, static_mode=static_mode, seed=21)
+    ss = {k: v.clone() for k, v in case["sd_static"].items()}
+    rays = case["rays"].clone().requires_grad_(True)
+    xyz, z, valid = O.sampleXYZ(case["cs"], rays, 48, ray_type, False)
+    fs = O.field_forward(case["cs"], ss, rays, case["ts"], xyz, z, valid, ray_type)
+    ws = _loss_weights([fs[7].shape, fs[6].shape, fs[4].shape, fs[9].shape], 5)
+    loss = (fs[7] * ws[0]).sum() + (fs[6] * ws[1]).sum() + (fs[4] * ws[2]).sum() + (fs[9] * ws[3]).sum()
+    loss.backward()
+
+    static, dyn = H.native_models(case, DEV)
+    rays2 = case["rays"].to(DEV).requires_grad_(True)
+    xyz2, z2, valid2 = R.sampleXYZ(static, rays2, 48, ray_type, False)
+    f2 = static(rays2, case["ts"].to(DEV), None, xyz2, z2, valid2, ray_type=ray_type)
+    loss2 = sum((t * w.to(DEV)).sum() for t, w in zip((f2[7], f2[6], f2[4], f2[9]), ws))
+    loss2.backward()
+    torch.cuda.synchronize()
+    ok, r, n_out = _grad_ok(rays2.grad.cpu(), rays.grad)
+    print("rays grad rel err", r, n_out)
+    assert ok
+
+
+@gpu
+@pytest.mark.parametrize("ray_type,white", [("ndc", False), ("ndc", True), ("contract", False), ("contract", True)])
+def test_composite_gradients(ray_type, white):
+    from dynrf_b200 import backward as B
+
+    g = torch.Generator().manual_seed(3)
+    n, s = 37, 150
+    rgb_s, rgb_d = torch.rand(n, s, 3, generator=g), torch.rand(n, s, 3, generator=g)
+    sig_s, sig_d = torch.relu(torch.randn(n, s, generator=g)) * 2, torch.relu(torch.randn(n, s, generator=g)) * 2
+    dists = torch.rand(n, s, generator=g) * 0.3
+    blend = torch.rand(n, s, generator=g)
+    z = torch.sort(torch.rand(n, s, generator=g), -1).values
+    rays, _ = H.synth_rays(n, ray_type, g)
+    ins = [rgb_s, sig_s, rgb_d, sig_d, dists, blend, z, rays]
+    a = [t.clone().requires_grad_(True) for t in ins]
+    o = O.raw2outputs(*a[:7], a[7], is_train=True, ray_type=ray_type, white_bg_draw=white)
+    ws = _loss_weights([t.shape for t in o], 17)
+    sum((t * w).sum() for t, w in zip(o, ws)).backward()
+
+    b = [t.clone().to(DEV).requires_grad_(True) for t in ins]
+    oo, wf, wsn, wd = B.CompositeFn.apply(*b, white, ray_type)
+    from dynrf_b200.autograd import _split_ray_out
+
+    rf, df, af, rs, ds, as_, rd, dd, ad, dyn = _split_ray_out(oo)
+    o2 = (rf, df, af, wf, rs, ds, as_, wsn, rd, dd, ad, wd, dyn)
+    for x, y in zip(o, o2):  # (1 - acc) * 256 in the contract depth maps amplifies 1-ulp differences of acc
+        torch.testing.assert_close(y.cpu(), x.detach(), rtol=1e-4, atol=1e-4 if ray_type == "contract" else 2e-5)
+    sum((t * w.to(DEV)).sum() for t, w in zip(o2, ws)).backward()
+    torch.cuda.synchronize()
+    names = ["rgb_s", "sigma_s", "rgb_d", "sigma_d", "dists", "blending", "z", "rays"]
+    for nme, x, y in zip(names, a, b):
+        if nme == "z":
+            continue
+        if nme == "rays":
+            # only the NDC background term (1 - acc) * (o_z + d_z) reaches rays; with acc ~ 1 it is O(1e-7) noise,
+            # so compare absolutely.  Contracted rays get no gradient from the compositing.
+            got = torch.zeros_like(x.grad) if y.grad is None else y.grad.cpu()
+            torch.testing.assert_close(got, x.grad, rtol=1e-3, atol=1e-5)
+            continue
+        ok, r, r2 = _grad_ok(y.grad.cpu(), x.grad)
+        print(nme, r, r2)
+        assert ok, (nme, r, r2)
+
+
+@gpu
+def test_reference_golden_gradients(golden_case):
+    """Parameter gradients against values produced by autograd through the UNMODIFIED reference."""
+    import renderer as R
+
+    g = golden_case
+    case = H.build_pair(list(g.raw["grid"]), 0, int(g.raw["n_samples"]), ray_type=g.meta["ray_type"],
+                        static_mode=g.meta["static_mode"], sd_static=g.sd("static"), sd_dynamic=g.sd("dynamic"),
+                        rays=g.t("rays"), ts=g.t("ts"), aabb=g.t("aabb"), near_far=tuple(float(v) for v in g.raw["near_far"]))
+    static, dyn, rays, fs, fd, o = _native_full(case)
+    gen = torch.Generator().manual_seed(20211202 + 13)
+    loss = 0.0
+    for t in o:
+        loss = loss + (t * torch.randn(t.shape, generator=gen).to(DEV)).sum()
+    loss = loss + (fd[5] * torch.randn(fd[5].shape, generator=gen).to(DEV)).sum() * 0.1
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(g.raw["g_loss"])) <= 1e-3
+    bad = {}
+    for tag, mod in (("s", static), ("d", dyn)):
+        for name, p in mod.named_parameters():
+            key = f"g_{tag}/{name}/abssum"
+            if key not in g.raw:
+                continue
+            got = float(p.grad.double().abs().sum())
+            want = float(g.raw[key])
+            if abs(got - want) > 2e-3 * max(want, 1e-6):
+                bad[f"{tag}:{name}"] = (got, want)
+    assert not bad, bad
