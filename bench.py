@@ -61,7 +61,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -194,12 +194,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # samples through warm-up + timed region (under load)
     for _ in range(args.warmup):
         one(rays_d, ts_d, target_d)
     barrier()
 
     # ---- device-resident timing
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     L.profile_events = {"dynrf_static_sigma_weight_fwd": [], "dynrf_dyn_sigma_blend_fwd": []}
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = L.launch_count
@@ -241,6 +241,10 @@ def main():
 
     if rank == 0:
         pk = peaks()
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_k1_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
         total_rays = N_RAYS * world * args.steps
         value = total_rays / (t_ms * 1e-3)
         e2e = total_rays / (t2_ms * 1e-3)
@@ -257,7 +261,7 @@ def main():
                        "l2": "512 MiB buffer rewritten between timed iterations (L2 flush); parameters 93 MB + per-sample tensors"},
             "roofline": {"kernel": "k_static_sigma_weight (static density + sigma->alpha + transmittance scan, a6+a8+a9)",
                          "bound": "hbm", "achieved": k1_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                         "frac": (k1_gbs / pk["hbm"]) if k1_gbs else None, "traffic": None,
+                         "frac": (k1_gbs / pk["hbm"]) if k1_gbs else None, "traffic": traffic,
                          "ms_per_launch": k1_ms, "bytes_per_sample": BYTES_PER_SAMPLE_K1, "peak_source": pk["src"],
                          "note": "algorithmic bytes (every tap counted); the 10 MB density tables are L2-resident so DRAM traffic is far lower -- see profiles/"},
             "roofline_dominant": {"kernel": "k_dyn_sigma_blend (a16+a17: 3-scale lookups + two 152->64->1 MLPs, fp32 FFMA)",

@@ -318,18 +318,9 @@ def train_step(step, rays, ts, target):
     loss = ((o[0] - target) ** 2).mean() + ((o[4] - target) ** 2).mean() + ((o[8] - target) ** 2).mean()
     step.opt.zero_grad(set_to_none=True)
     loss.backward()
-    if step.world > 1:
-        import torch.distributed as dist
+    from .parallel import allreduce_mean_grads
 
-        grads = [p.grad for p in step.params if p.grad is not None]
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat)
-        flat /= step.world
-        off = 0
-        for g in grads:
-            k = g.numel()
-            g.copy_(flat[off:off + k].view_as(g))
-            off += k
+    allreduce_mean_grads(step.params, step.world)
     step.opt.step()
     out = torch.cat((o[0], o[1][:, None], o[2][:, None], o[4], o[5][:, None], o[6][:, None], o[8], o[9][:, None],
                      o[10][:, None], o[12][:, None]), -1).detach()

@@ -32,14 +32,9 @@ class Step:
         self.gather_buf = None
 
     def _gather(self, out):
-        if self.world > 1:
-            import torch.distributed as dist
+        from .parallel import gather_ray_maps
 
-            if self.gather_buf is None or self.gather_buf.shape[0] != out.shape[0] * self.world:
-                self.gather_buf = torch.empty(out.shape[0] * self.world, out.shape[1], device=out.device)
-            dist.all_gather_into_tensor(self.gather_buf, out)
-            return self.gather_buf
-        return out
+        return gather_ray_maps(out, self.world)
 
     @torch.no_grad()
     def forward_fused(self, rays, ts):
