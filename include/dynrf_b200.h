@@ -230,6 +230,29 @@ int dynrf_warp_bwd(const dynrf_field_cfg_t* cfg, const float* xyz, int N, int S,
 int dynrf_time_embed_bwd(const float* ts, int N, const dynrf_layer_t* l1, const dynrf_layer_t* l2, const float* gtout,
                          const dynrf_layer_grad_t* g1, const dynrf_layer_grad_t* g2, void* stream);
 
+/* ---- tensor-core (tcgen05 / TMEM / TMA) variants of the MLP-bearing forward stages ----------------
+ * A "UMMA-packed" nn.Linear: weight [N][K] pre-split into tf32 hi/lo parts and laid out per 32-column chunk as
+ * [hi: Npad x 32][lo: Npad x 32] in the K-major no-swizzle operand layout (dynrf_pack_linear_umma);
+ * Npad = round_up(N,8), nchunks = ceil(K/32); wq holds nchunks*2*Npad*32 floats, bias Npad floats. */
+typedef struct {
+  const float* wq;
+  const float* bias;
+  int32_t K, N, Npad, nchunks;
+} dynrf_umma_layer_t;
+int dynrf_pack_linear_umma(const float* w, const float* bias_or_null, int N, int K, float* wq, float* bias_out, void* stream);
+/* same contracts as dynrf_warp_fwd / dynrf_dyn_sigma_blend_fwd; 3-pass split-TF32 MMAs, fp32 accumulation in TMEM */
+int dynrf_warp_fwd_tc(const dynrf_field_cfg_t* cfg, const float* xyz, int N, int S, const float* tfeat,
+                      const dynrf_umma_layer_t* layer3, const dynrf_umma_layer_t* layer4, const dynrf_layer_t* layer5,
+                      float* xyz_prime, void* stream);
+int dynrf_dyn_sigma_blend_fwd_tc(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density, const dynrf_vm_t* blending,
+                                 const dynrf_umma_layer_t* d1, const dynrf_layer_t* d2, const dynrf_umma_layer_t* b1,
+                                 const dynrf_layer_t* b2, const float* xyz, const float* xyz_prime, const uint8_t* valid,
+                                 const float* tfeat, int N, int S, float* sigma, float* blend, void* stream);
+
+/* Self-test of the tcgen05 tile-GEMM building block: C[128][N] = A[128][K] x B[N][K]^T, N in {32,64,128},
+ * passes = 1 (TF32) or 3 (split TF32, ~fp32 accuracy).  Used by tests/test_gpu_umma.py. */
+int dynrf_selftest_umma_gemm(const float* A, const float* B, int K, int N, int passes, float* C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,7 @@ PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # robust
 CSRC = os.path.join(PKG_ROOT, "csrc")
 LIB_DIR = os.path.join(PKG_ROOT, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdynrf_b200.so")
-SOURCES = ["ray_kernels.cu", "field_kernels.cu", "backward_kernels.cu"]
+SOURCES = ["ray_kernels.cu", "field_kernels.cu", "backward_kernels.cu", "selftest.cu", "tc_kernels.cu"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -74,6 +74,14 @@ _P, _I, _F = C.c_void_p, C.c_int, C.c_float
 _cfg, _vm, _ly, _vg = C.POINTER(FieldCfgT), C.POINTER(VmT), C.POINTER(LayerT), C.POINTER(VmGradT)
 _lg = C.POINTER(LayerGradT)
 
+
+class UmmaLayerT(C.Structure):
+    _fields_ = [("wq", C.c_void_p), ("bias", C.c_void_p), ("K", C.c_int32), ("N", C.c_int32), ("Npad", C.c_int32),
+                ("nchunks", C.c_int32)]
+
+
+_ul = C.POINTER(UmmaLayerT)
+
 # name -> argtypes; every entry point include/dynrf_b200.h declares (tests check the two lists agree)
 PROTOTYPES = {
     "dynrf_abi_version": [],
@@ -104,6 +112,10 @@ PROTOTYPES = {
     "dynrf_dyn_mlp_bwd": [_cfg, _I, _vm, _vg, _ly, _ly, _P, _P, _P, _P, _P, _I, _I, _P, _lg, _lg, _P, _P],
     "dynrf_warp_bwd": [_cfg, _P, _I, _I, _P, _ly, _ly, _ly, _P, _P, _P, _lg, _lg, _lg, _P, _P],
     "dynrf_time_embed_bwd": [_P, _I, _ly, _ly, _P, _lg, _lg, _P],
+    "dynrf_selftest_umma_gemm": [_P, _P, _I, _I, _I, _P, _P],
+    "dynrf_pack_linear_umma": [_P, _P, _I, _I, _P, _P, _P],
+    "dynrf_warp_fwd_tc": [_cfg, _P, _I, _I, _P, _ul, _ul, _ly, _P, _P],
+    "dynrf_dyn_sigma_blend_fwd_tc": [_cfg, _vm, _vm, _ul, _ly, _ul, _ly, _P, _P, _P, _P, _I, _I, _P, _P, _P],
 }
 
 _lib = None

@@ -108,6 +108,48 @@ class PackedLayer:
         return self.struct
 
 
+class PackedUmmaLayer:
+    """nn.Linear weight pre-split (tf32 hi/lo) and laid out for the tcgen05 path; repacked on version change."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor]):
+        self.weight, self.bias = weight, bias
+        self.N, self.K = weight.shape
+        self.Npad = (self.N + 7) // 8 * 8
+        self.nchunks = (self.K + 31) // 32
+        self.wq = torch.empty(self.nchunks * 2 * self.Npad * 32, device=weight.device, dtype=torch.float32)
+        self.b = torch.empty(self.Npad, device=weight.device, dtype=torch.float32)
+        self._key = None
+        self.struct = L.UmmaLayerT(self.wq.data_ptr(), self.b.data_ptr(), self.K, self.N, self.Npad, self.nchunks)
+
+    def refresh(self) -> L.UmmaLayerT:
+        key = (self.weight.data_ptr(), self.weight._version, None if self.bias is None else self.bias._version)
+        if key != self._key:
+            w = _f32c(self.weight.detach())
+            b = None if self.bias is None else _f32c(self.bias.detach())
+            L.check(L.load().dynrf_pack_linear_umma(_p(w), _p(b), self.N, self.K, _p(self.wq), _p(self.b), _stream()),
+                    "dynrf_pack_linear_umma")
+            self._key = key
+        return self.struct
+
+
+# tensor-core (tcgen05) kernels for the MLP stages that have them; the SIMT fp32 kernels stay in the library
+# as a cross-check (tests flip this flag to compare the two)
+USE_TC = True
+
+
+def umma_layers(m, names):
+    cache = m.__dict__.setdefault("_packed_umma", {})
+    tbl = m._layer_table()
+    out = {}
+    for n in names:
+        lin = tbl[n]
+        pl = cache.get(n)
+        if pl is None or pl.weight is not lin.weight or pl.bias is not lin.bias:
+            pl = cache[n] = PackedUmmaLayer(lin.weight, lin.bias)
+        out[n] = pl.refresh()
+    return out
+
+
 def field_cfg(aabb: torch.Tensor, near_far, distance_scale, weight_thres, act: str, density_shift, ray_type: str) -> L.FieldCfgT:
     a = aabb.detach().cpu().tolist()
     cfg = L.FieldCfgT()
@@ -217,15 +259,23 @@ def dynamic_forward_raw(m, rays, ts, xyz, z_vals, valid, ray_type):
     L.check(lib.dynrf_time_embed_fwd(_p(ts), n, C.byref(ly["layer1"]), C.byref(ly["layer2"]), _p(tfeat), _stream()),
             "dynrf_time_embed_fwd")
     xyz_prime = torch.empty(n, s, 3, device=dev)
-    L.check(lib.dynrf_warp_fwd(C.byref(cfg), _p(xyz), n, s, _p(tfeat), C.byref(ly["layer3"]), C.byref(ly["layer4"]),
-                               C.byref(ly["layer5"]), _p(xyz_prime), _stream()), "dynrf_warp_fwd")
     sigma = torch.empty(n, s, device=dev)
     blend = torch.empty(n, s, device=dev)
     vden = vm_struct(m.density_plane, m.density_line)
     vbl = vm_struct(m.blending_plane, m.blending_line)
-    L.check(lib.dynrf_dyn_sigma_blend_fwd(C.byref(cfg), C.byref(vden), C.byref(vbl), C.byref(ly["d1"]), C.byref(ly["d2"]),
-                                          C.byref(ly["b1"]), C.byref(ly["b2"]), _p(xyz), _p(xyz_prime), _p(valid_u8), _p(tfeat),
-                                          n, s, _p(sigma), _p(blend), _stream()), "dynrf_dyn_sigma_blend_fwd")
+    if USE_TC:
+        ul = umma_layers(m, ("layer3", "layer4", "d1", "b1"))
+        L.check(lib.dynrf_warp_fwd_tc(C.byref(cfg), _p(xyz), n, s, _p(tfeat), C.byref(ul["layer3"]), C.byref(ul["layer4"]),
+                                      C.byref(ly["layer5"]), _p(xyz_prime), _stream()), "dynrf_warp_fwd_tc")
+        L.check(lib.dynrf_dyn_sigma_blend_fwd_tc(C.byref(cfg), C.byref(vden), C.byref(vbl), C.byref(ul["d1"]), C.byref(ly["d2"]),
+                                                 C.byref(ul["b1"]), C.byref(ly["b2"]), _p(xyz), _p(xyz_prime), _p(valid_u8),
+                                                 _p(tfeat), n, s, _p(sigma), _p(blend), _stream()), "dynrf_dyn_sigma_blend_fwd_tc")
+    else:
+        L.check(lib.dynrf_warp_fwd(C.byref(cfg), _p(xyz), n, s, _p(tfeat), C.byref(ly["layer3"]), C.byref(ly["layer4"]),
+                                   C.byref(ly["layer5"]), _p(xyz_prime), _stream()), "dynrf_warp_fwd")
+        L.check(lib.dynrf_dyn_sigma_blend_fwd(C.byref(cfg), C.byref(vden), C.byref(vbl), C.byref(ly["d1"]), C.byref(ly["d2"]),
+                                              C.byref(ly["b1"]), C.byref(ly["b2"]), _p(xyz), _p(xyz_prime), _p(valid_u8),
+                                              _p(tfeat), n, s, _p(sigma), _p(blend), _stream()), "dynrf_dyn_sigma_blend_fwd")
     weight = torch.empty(n, s, device=dev)
     dists = torch.empty(n, s, device=dev)
     rgb = torch.empty(n, s, 3, device=dev)

@@ -132,3 +132,23 @@ def test_octree_render_signature():
     with torch.no_grad():
         out_s = R.OctreeRender_trilinear_fast(rays, ts, None, static, xyz, z, valid, chunk=32, N_samples=16, device=DEV)
     assert out_s[2] is None and out_s[5] is None and out_s[8].shape == (50, 16)
+
+
+@gpu
+def test_tensor_core_path_matches_simt_path():
+    """tcgen05 (split-TF32, TMEM) kernels vs the fp32 SIMT kernels of the same stages: same sigma / blending / xyz_prime."""
+    from dynrf_b200 import ops
+
+    case = H.build_pair([37, 41, 29], 300, 77, seed=9)
+    models = H.native_models(case, DEV)
+    try:
+        ops.USE_TC = True
+        a = H.native_pass(case, DEV, models)
+        ops.USE_TC = False
+        b = H.native_pass(case, DEV, models)
+    finally:
+        ops.USE_TC = True
+    for i, name in ((7, "sigma"), (2, "blending"), (5, "xyz_prime"), (4, "weight")):
+        d = float((a["fd"][i] - b["fd"][i]).abs().max())
+        print(name, d)
+        assert d <= 5e-6, (name, d)
