@@ -249,9 +249,30 @@ int dynrf_dyn_sigma_blend_fwd_tc(const dynrf_field_cfg_t* cfg, const dynrf_vm_t*
                                  const dynrf_layer_t* b2, const float* xyz, const float* xyz_prime, const uint8_t* valid,
                                  const float* tfeat, int N, int S, float* sigma, float* blend, void* stream);
 
+/* v2 of the tensor-core density + blending stage: operands produced directly in the split K-major layout, the
+ * shared position/time rows multiplied once against [density | blending] layer-1 weights (N = 128), 512 threads,
+ * 3-deep operand ring + 2 TMA weight slots.  wq: dynrf_sb_umma_floats() floats built by dynrf_pack_sb_umma from the two
+ * layer-1 weights [64][152]; b1cat [128] = [b1_density | b1_blending]; w2cat [128] = layer-2 weights; b2cat [2]. */
+int dynrf_sb_umma_floats(void);
+int dynrf_pack_sb_umma(const float* w1_density, const float* w1_blending, float* wq, void* stream);
+int dynrf_dyn_sigma_blend_fwd_tc2(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density, const dynrf_vm_t* blending,
+                                  const float* wq, const float* b1cat, const float* w2cat, const float* b2cat,
+                                  const float* xyz, const float* xyz_prime, const uint8_t* valid, const float* tfeat, int N,
+                                  int S, float* sigma, float* blend, void* stream);
+
+/* Weight-gradient GEMM on tensor cores (3-pass split TF32, fp32 TMEM accumulation):
+ *   dw[n * dw_ld + k] += sum_{p < P} XT[k * ldx + p] * DYT[n * ldy + p],  k < K <= 256, n < N <= 128,
+ * P = min(*count_ptr, Pmax) (count_ptr may be NULL).  XT / DYT: feature-major activations / output gradients written by the
+ * fused backward kernels; 16-byte aligned, ldx / ldy multiples of 4. */
+int dynrf_wgrad_gemm(const float* XT, int ldx, int K, const float* DYT, int ldy, int N, int Pmax, const int32_t* count_ptr,
+                     float* dw, int dw_ld, void* stream);
+
 /* Self-test of the tcgen05 tile-GEMM building block: C[128][N] = A[128][K] x B[N][K]^T, N in {32,64,128},
  * passes = 1 (TF32) or 3 (split TF32, ~fp32 accuracy).  Used by tests/test_gpu_umma.py. */
 int dynrf_selftest_umma_gemm(const float* A, const float* B, int K, int N, int passes, float* C, void* stream);
+/* transposed product on forward-style operands (the weight-gradient form): C[128][64] (rows k < K valid) =
+ * A[128][K]^T x B[128][64], operands read MN-major; passes 1 (hi*hi) or 2 (+ hi*lo). */
+int dynrf_selftest_umma_wgrad(const float* A, const float* B, int K, int passes, float* C, void* stream);
 
 #ifdef __cplusplus
 }

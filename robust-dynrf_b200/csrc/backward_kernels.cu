@@ -393,7 +393,7 @@ struct LayerGrad {
 
 constexpr size_t kWarpBwdSmem = (size_t)(96 * kBL + 64 * kBL + 64 * kBL + 2 * kChunkK * 64) * sizeof(float) + sizeof(BScratch);
 
-__global__ void __launch_bounds__(kMlpThreads)
+__global__ void __launch_bounds__(kMlpThreads, 2)
 k_warp_bwd(dynrf_field_cfg_t cfg, const float* __restrict__ xyz, int P, int S, const float* __restrict__ tfeat, dynrf_layer_t l3,
            dynrf_layer_t l4, dynrf_layer_t l5, const float* __restrict__ wb4 /*[64][64]*/, const float* __restrict__ wb3t /*[64][32]*/,
            const float* __restrict__ gxp, LayerGrad g3, LayerGrad g4, LayerGrad g5, float* __restrict__ gtout) {
@@ -561,7 +561,7 @@ k_time_embed_bwd(const float* __restrict__ ts, int N, dynrf_layer_t l1, dynrf_la
 
 constexpr size_t kDmSmem = (size_t)(152 * kBL + 64 * kBL + 80 * kBL + 2 * kChunkK * 80) * sizeof(float) + sizeof(BScratch);
 
-__global__ void __launch_bounds__(kMlpThreads)
+__global__ void __launch_bounds__(kMlpThreads, 2)
 k_dyn_mlp_bwd(dynrf_field_cfg_t cfg, int mode, dynrf_vm_t vm, dynrf_vm_grad_t gvm, dynrf_layer_t l1, dynrf_layer_t l2,
               const float* __restrict__ wb1f /*[64][80]*/, const float* __restrict__ xyz, const float* __restrict__ xyz_prime,
               const uint8_t* __restrict__ valid, const float* __restrict__ tfeat, int P, int S, const float* __restrict__ gout,

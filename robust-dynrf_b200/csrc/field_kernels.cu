@@ -427,7 +427,7 @@ int dynrf_warp_fwd(const dynrf_field_cfg_t* cfg, const float* xyz, int N, int S,
   DYNRF_TRY(set_smem(k_warp, kWarpSmem));
   const int P = N * S;
   const int ntiles = (P + kTileM - 1) / kTileM;
-  const int grid = min(ntiles, sm_count());
+  const int grid = min(ntiles, 2 * sm_count());
   k_warp<<<grid, kMlpThreads, kWarpSmem, S_(stream)>>>(*cfg, xyz, P, S, tfeat, *l3, *l4, *l5, xyz_prime);
   DYNRF_CHECK_LAUNCH();
   return 0;

@@ -324,6 +324,396 @@ k_warp_tc(dynrf_field_cfg_t cfg, const float* __restrict__ xyz, int P, int S, co
   if (warp == 0) umma::tmem_dealloc(pipe.tmem, 128);
 }
 
+// ================================================================================================
+// v2: dynamic density + blending, producers write the split K-major operand directly (no fp32 staging),
+// the shared position/time rows are multiplied once against the concatenated [density | blending] weights
+// (N = 128), 512 threads, ring of 3 operand buffers + 2 TMA weight slots so the asynchronous MMAs and
+// weight copies overlap the gathers of the next chunk.
+//
+// K order (this kernel's own; the pack kernel permutes the reference's columns accordingly):
+//   chunk 0..2  position/time rows, 20 quads of 4:
+//       quad 0            : xn0 xn1 xn2 t
+//       quads 1+5d .. 5+5d: dim d: [sin f0-3] [cos f0-3] [sin f4-7] [cos f4-7] [sin f8, sin f9, cos f8, cos f9]
+//       quads 16..19      : [sin t f0-3] [sin t f4-7] [cos t f0-3] [cos t f4-7]
+//   chunk 3+2si   density  features of stride 2^si (24 rows, reference order)   -> TMEM columns   0..63
+//   chunk 4+2si   blending features of stride 2^si                              -> TMEM columns  64..127
+
+constexpr int kTcThreads = 512;
+constexpr int kOpFloats = 2 * kKC * kTileM;  // hi + lo, 32 rows x 128 samples
+constexpr int kOpLo = kKC * kTileM;          // float offset of the lo half
+constexpr int kWSlotFloats = 2 * 128 * kKC;  // largest weight chunk (N = 128, 32 rows)
+constexpr int kSbChunks = 9;
+
+__host__ __device__ constexpr int sb_rows(int j) { return j < 2 ? 32 : (j == 2 ? 16 : 24); }
+__host__ __device__ constexpr int sb_n(int j) { return j < 3 ? 128 : 64; }
+__host__ __device__ constexpr int sb_woff(int j) {  // float offset of chunk j's weight blob
+  int o = 0;
+  for (int i = 0; i < j; ++i) o += 2 * sb_n(i) * sb_rows(i);
+  return o;
+}
+constexpr int kSbWFloats = sb_woff(kSbChunks);
+
+struct TapF {
+  int i0, i1;
+  float w0, w1;
+};
+__device__ __forceinline__ TapF tapf(float x, int n, int s) {
+  const Tap1 t = make_tap(x, n, s);
+  return TapF{t.i0, t.i1, t.w0, t.w1};
+}
+__device__ __forceinline__ float4 vm_group_f(const float* __restrict__ plane, const float* __restrict__ line, int C, int W,
+                                             const TapF& tu, const TapF& tv, const TapF& tl, int c) {
+  const float wnw = tu.w0 * tv.w0, wne = tu.w1 * tv.w0, wsw = tu.w0 * tv.w1, wse = tu.w1 * tv.w1;
+  const size_t r0 = (size_t)tv.i0 * W, r1 = (size_t)tv.i1 * W;
+  float4 p = mul4(ldg4(plane + (r0 + tu.i0) * C + c), wnw);
+  p = fma4(ldg4(plane + (r0 + tu.i1) * C + c), wne, p);
+  p = fma4(ldg4(plane + (r1 + tu.i0) * C + c), wsw, p);
+  p = fma4(ldg4(plane + (r1 + tu.i1) * C + c), wse, p);
+  float4 l = mul4(ldg4(line + (size_t)tl.i0 * C + c), tl.w0);
+  l = fma4(ldg4(line + (size_t)tl.i1 * C + c), tl.w1, l);
+  return mul44(p, l);
+}
+
+// write 4 consecutive operand rows (quad q of the chunk) for sample m as split tf32, one 16-byte store each
+__device__ __forceinline__ void store_quad(float* __restrict__ buf, int m, int q, float4 v) {
+  float4 hi, lo;
+  umma::split_tf32(v.x, hi.x, lo.x);
+  umma::split_tf32(v.y, hi.y, lo.y);
+  umma::split_tf32(v.z, hi.z, lo.z);
+  umma::split_tf32(v.w, hi.w, lo.w);
+  const uint32_t off = umma::kmajor_off(m, q * 4, kTileM) >> 2;
+  *reinterpret_cast<float4*>(buf + off) = hi;
+  *reinterpret_cast<float4*>(buf + kOpLo + off) = lo;
+}
+
+__device__ __forceinline__ void sincos4(float x, float base, float4& s, float4& c) {
+  sincosf(x * base, &s.x, &c.x);
+  sincosf(x * (base * 2.f), &s.y, &c.y);
+  sincosf(x * (base * 4.f), &s.z, &c.z);
+  sincosf(x * (base * 8.f), &s.w, &c.w);
+}
+
+// position/time operand rows, unit u of 14 (see K order above); writes into the chunk buffer that holds its quads
+struct PosUnits {
+  // unit -> (chunk, first quad within chunk); units 0..4 in chunk 0, 5..9 in chunk 1, 10..13 in chunk 2
+};
+
+__device__ __forceinline__ void produce_pos_unit(int u, const TileScratch<kTileM>& scr, const float* __restrict__ tfeat, int m,
+                                                 float* __restrict__ buf) {
+  // chunk 0: u0 quad0 | u1 (d0,fq0) quads1,2 | u2 (d0,fq1) quads3,4 | u3 (d0,tail) quad5 | u4 (d1,fq0) quads6,7
+  // chunk 1: u5 (d1,fq1) quads0,1 | u6 (d1,tail) quad2 | u7 (d2,fq0) quads3,4 | u8 (d2,fq1) quads5,6 | u9 (d2,tail) quad7
+  // chunk 2: u10..u13 time quads 0..3
+  const int ry = scr.ray[m];
+  if (u == 0) {
+    const float t = ry >= 0 ? __ldg(tfeat + (size_t)ry * kTFeat) : 0.f;
+    store_quad(buf, m, 0, make_float4(scr.xn[0][m], scr.xn[1][m], scr.xn[2][m], t));
+    return;
+  }
+  if (u >= 10) {
+    const int tq = u - 10;  // 0: sin f0-3, 1: sin f4-7, 2: cos f0-3, 3: cos f4-7   (tfeat cols 1..8 sin, 9..16 cos)
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ry >= 0) {
+      const float* p = tfeat + (size_t)ry * kTFeat + 1 + tq * 4;
+      v = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+    }
+    store_quad(buf, m, tq, v);
+    return;
+  }
+  // (dim, kind) and destination quad
+  int d, kind, q;  // kind 0: fq0, 1: fq1, 2: tail
+  switch (u) {
+    case 1: d = 0; kind = 0; q = 1; break;
+    case 2: d = 0; kind = 1; q = 3; break;
+    case 3: d = 0; kind = 2; q = 5; break;
+    case 4: d = 1; kind = 0; q = 6; break;
+    case 5: d = 1; kind = 1; q = 0; break;
+    case 6: d = 1; kind = 2; q = 2; break;
+    case 7: d = 2; kind = 0; q = 3; break;
+    case 8: d = 2; kind = 1; q = 5; break;
+    default: d = 2; kind = 2; q = 7; break;
+  }
+  const float x = scr.xn[d][m];
+  if (kind == 2) {
+    float s8, c8, s9, c9;
+    sincosf(x * 256.f, &s8, &c8);
+    sincosf(x * 512.f, &s9, &c9);
+    store_quad(buf, m, q, make_float4(s8, s9, c8, c9));
+  } else {
+    float4 s, c;
+    sincos4(x, kind == 0 ? 1.f : 16.f, s, c);
+    store_quad(buf, m, q, s);
+    store_quad(buf, m, q + 1, c);
+  }
+}
+
+struct Ring {
+  uint64_t* bar_free;  // [3] operand buffer consumed (MMAs of the chunk that used it completed)
+  uint64_t* bar_w;     // [2] weight slot landed
+  float* abuf;         // 3 x kOpFloats
+  float* wbuf;         // 2 x kWSlotFloats
+  uint32_t chunk;      // running chunk counter, identical in every thread
+  uint32_t tmem;
+};
+
+__device__ __forceinline__ void ring_wait_free(const Ring& r) {
+  const uint32_t b = r.chunk % 3, u = r.chunk / 3;
+  if (u > 0) umma::mbar_wait(&r.bar_free[b], (u - 1) & 1);
+}
+__device__ __forceinline__ float* ring_abuf(const Ring& r) { return r.abuf + (size_t)(r.chunk % 3) * kOpFloats; }
+
+// tid 0: weights of chunk `c` (global blob) -> slot c & 1.  The slot was last read by chunk c-2.
+__device__ __forceinline__ void ring_prefetch_w(const Ring& r, uint32_t c, const float* blob, uint32_t bytes) {
+  if (c >= 2) {
+    const uint32_t pc = c - 2;
+    umma::mbar_wait(&r.bar_free[pc % 3], (pc / 3) & 1);
+  }
+  mbar_expect_tx(&r.bar_w[c & 1], bytes);
+  tma_load_1d(r.wbuf + (size_t)(c & 1) * kWSlotFloats, blob, bytes, &r.bar_w[c & 1]);
+}
+
+// tid 0: wait for this chunk's weights, issue the 3-pass MMAs, commit to the operand buffer's barrier
+template <int N>
+__device__ __forceinline__ void ring_issue(const Ring& r, int rows, uint32_t col0, bool first) {
+  const uint32_t c = r.chunk;
+  umma::mbar_wait(&r.bar_w[c & 1], (c >> 1) & 1);
+  umma::fence_after_sync();
+  const uint32_t idesc = umma::make_idesc_tf32(kTileM, N);
+  const uint32_t sa_hi = umma::smem_u32(r.abuf + (size_t)(c % 3) * kOpFloats), sa_lo = sa_hi + kOpLo * 4;
+  const uint32_t sb_hi = umma::smem_u32(r.wbuf + (size_t)(c & 1) * kWSlotFloats), sb_lo = sb_hi + N * rows * 4;
+#pragma unroll
+  for (int ps = 0; ps < 3; ++ps) {
+    const uint32_t sa = (ps == 2) ? sa_lo : sa_hi;
+    const uint32_t sb = (ps == 1) ? sb_lo : sb_hi;
+    for (int j = 0; j < rows / 8; ++j) {
+      const uint64_t da = umma::make_desc(sa + 2 * j * (kTileM * 16), kTileM * 16, 128);
+      const uint64_t db = umma::make_desc(sb + 2 * j * (N * 16), N * 16, 128);
+      umma::mma_tf32(r.tmem + col0, da, db, idesc, (!first || ps > 0 || j > 0) ? 1u : 0u);
+    }
+  }
+  umma::commit(&r.bar_free[c % 3]);
+}
+
+// ---- v3: warp-specialised.  16 producer warps (512 threads, 4 per sample) fill the operand ring and signal a
+// per-buffer "full" mbarrier; one extra warp owns the tensor core: it waits for "full" + the TMA'd weights, issues
+// the 3-pass MMAs, commits to the buffer's "free" barrier and prefetches the next weight chunk.  No CTA-wide
+// barrier in the steady state; producers use a named barrier (id 1) among themselves for the per-tile scratch.
+// The bilinear taps depend only on (axis, stride) -- 9 per sample -- and are computed once per tile into shared memory.
+
+constexpr int kProdThreads = 512;
+constexpr int kTc3Threads = kProdThreads + 32;
+
+struct TapsSmem {
+  int4 t[9][kTileM];  // [stride*3 + axis][sample]: (i0, i1, w0 bits, w1 bits)
+};
+
+__device__ __forceinline__ TapF load_tap(const TapsSmem& ts, int si, int axis, int m) {
+  const int4 v = ts.t[si * 3 + axis][m];
+  return TapF{v.x, v.y, __int_as_float(v.z), __int_as_float(v.w)};
+}
+
+__device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 1, %0;\n" ::"n"(kProdThreads) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+
+constexpr size_t kSb2Smem = (size_t)(3 * kOpFloats + 2 * kWSlotFloats + 4 * kTileM + 256) * sizeof(float) + sizeof(TapsSmem) +
+                            sizeof(TileScratch<kTileM>) + 128;
+
+__global__ void __launch_bounds__(kTc3Threads, 1)
+k_dyn_sigma_blend_tc2(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, const float* __restrict__ wq /*kSbWFloats*/,
+                      const float* __restrict__ b1cat /*[128]*/, const float* __restrict__ w2cat /*[128]*/, const float* __restrict__ b2cat /*[2]*/,
+                      const float* __restrict__ xyz, const float* __restrict__ xyz_prime, const uint8_t* __restrict__ valid,
+                      const float* __restrict__ tfeat, int P, int S, float* __restrict__ sigma, float* __restrict__ blend) {
+  extern __shared__ __align__(128) float smem[];
+  float* abuf = smem;
+  float* wbuf = abuf + 3 * kOpFloats;
+  float* part = wbuf + 2 * kWSlotFloats;  // [4][128] partial dots
+  float* cst = part + 4 * kTileM;         // b1cat[128] | w2cat[128]
+  TapsSmem& taps = *reinterpret_cast<TapsSmem*>(cst + 256);
+  TileScratch<kTileM>& scr = *reinterpret_cast<TileScratch<kTileM>*>(reinterpret_cast<uint8_t*>(&taps) + sizeof(TapsSmem));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(&scr) + sizeof(TileScratch<kTileM>));
+  uint64_t* bar_free = bars;      // [3]
+  uint64_t* bar_w = bars + 3;     // [2]
+  uint64_t* bar_full = bars + 5;  // [3]
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) umma::mbar_init(&bars[i], 1);
+    for (int i = 0; i < 3; ++i) umma::mbar_init(&bar_full[i], kProdThreads / 32);
+    umma::fence_mbar_init();
+  }
+  if (tid < 128) cst[tid] = __ldg(b1cat + tid);
+  else if (tid < 256) cst[tid] = __ldg(w2cat + tid - 128);
+  if (warp == 0) umma::tmem_alloc(tslot, 128);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  Ring ring{bar_free, bar_w, abuf, wbuf, 0u, *tslot};
+  const int ntiles = (P + kTileM - 1) / kTileM;
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t total_chunks = (uint32_t)my_tiles * kSbChunks;
+
+  if (warp == kProdThreads / 32) {
+    // ===================== tensor-core warp =====================
+    if (lane == 0 && total_chunks > 0) {
+      ring_prefetch_w(ring, 0, wq + sb_woff(0), 2u * sb_n(0) * sb_rows(0) * 4u);
+      for (uint32_t c = 0; c < total_chunks; ++c) {
+        const int j = (int)(c % kSbChunks);
+        ring.chunk = c;
+        umma::mbar_wait(&bar_full[c % 3], (c / 3) & 1);
+        const uint32_t col0 = (j >= 3 && ((j - 3) & 1)) ? 64u : 0u;
+        if (j < 3) ring_issue<128>(ring, sb_rows(j), 0u, j == 0);
+        else ring_issue<64>(ring, sb_rows(j), col0, false);
+        if (c + 1 < total_chunks) {
+          const int nj = (j + 1) % kSbChunks;
+          ring_prefetch_w(ring, c + 1, wq + sb_woff(nj), 2u * sb_n(nj) * sb_rows(nj) * 4u);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== producer / epilogue warps =====================
+    const int m = tid & (kTileM - 1), prt = tid >> 7;
+    const AabbNorm nb = make_norm(cfg);
+    const int G[3] = {vden.W[0], vden.H[0], vden.L[0]};
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      if (tid < kTileM) {
+        const int i = tile * kTileM + tid;
+        const bool in = i < P;
+        scr.ray[tid] = in ? i / S : -1;
+        scr.on[tid] = (in && valid[i] != 0) ? 1 : 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float x = in ? __ldg(xyz + (size_t)i * 3 + a) : 0.f;
+          const float xp = in ? __ldg(xyz_prime + (size_t)i * 3 + a) : 0.f;
+          scr.xn[a][tid] = norm_coord(x, nb.mn[a], nb.inv[a]);
+          scr.xq[a][tid] = norm_coord(xp, nb.mn[a], nb.inv[a]);
+        }
+      }
+      prod_bar();
+      // 9 taps per sample: (stride, axis)
+      for (int item = tid; item < 9 * kTileM; item += kProdThreads) {
+        const int mm = item & (kTileM - 1), t = item >> 7;
+        const int si = t / 3, ax = t % 3;
+        const Tap1 tp = make_tap(scr.xq[ax][mm], ax == 0 ? G[0] : (ax == 1 ? G[1] : G[2]), 1 << si);
+        taps.t[t][mm] = make_int4(tp.i0, tp.i1, __float_as_int(tp.w0), __float_as_int(tp.w1));
+      }
+      prod_bar();
+      const bool act = scr.on[m] != 0;
+#pragma unroll 1
+      for (int j = 0; j < kSbChunks; ++j) {
+        ring_wait_free(ring);
+        float* buf = ring_abuf(ring);
+        if (j < 3) {
+          const int u0 = j * 5, nu = (j == 2) ? 4 : 5;
+          for (int u = prt; u < nu; u += 4) produce_pos_unit(u0 + u, scr, tfeat, m, buf);
+        } else {
+          const int si = (j - 3) >> 1;
+          const bool isbl = ((j - 3) & 1) != 0;
+          {
+            const float* pp = isbl ? vbl.plane[0] : vden.plane[0];
+            const float* ll = isbl ? vbl.line[0] : vden.line[0];
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (act) r = vm_group_f(pp, ll, 16, G[0], load_tap(taps, si, 0, m), load_tap(taps, si, 1, m), load_tap(taps, si, 2, m), prt * 4);
+            store_quad(buf, m, prt, r);
+          }
+          if (prt < 2) {
+            const float* pp = prt == 0 ? (isbl ? vbl.plane[1] : vden.plane[1]) : (isbl ? vbl.plane[2] : vden.plane[2]);
+            const float* ll = prt == 0 ? (isbl ? vbl.line[1] : vden.line[1]) : (isbl ? vbl.line[2] : vden.line[2]);
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            // plane 1: (u,v,l) = (x,z,y), W = Gx; plane 2: (y,z,x), W = Gy
+            if (act)
+              r = vm_group_f(pp, ll, 4, prt == 0 ? G[0] : G[1], load_tap(taps, si, prt == 0 ? 0 : 1, m), load_tap(taps, si, 2, m),
+                             load_tap(taps, si, prt == 0 ? 1 : 0, m), 0);
+            store_quad(buf, m, 4 + prt, r);
+          }
+        }
+        umma::fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_full[ring.chunk % 3]);
+        ring.chunk++;
+      }
+      // accumulators complete when the last chunk's commit lands (tcgen05 ops retire in order)
+      {
+        const uint32_t lc = ring.chunk - 1;
+        umma::mbar_wait(&bar_free[lc % 3], (lc / 3) & 1);
+        umma::fence_after_sync();
+      }
+      {
+        const int q = warp & 3, cb = warp >> 2;  // lane quadrant, 32-column block (0,1: density  2,3: blending)
+        float r[32];
+        umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 32, r);
+        float acc = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const int n = cb * 32 + jj;
+          acc = fmaf(fmaxf(r[jj] + cst[n], 0.f), cst[128 + n], acc);
+        }
+        part[cb * kTileM + q * 32 + lane] = acc;
+      }
+      umma::fence_before_sync();
+      prod_bar();
+      if (tid < 2 * kTileM) {
+        const int which = tid >> 7, mm = tid & (kTileM - 1);
+        const int i = tile * kTileM + mm;
+        if (i < P) {
+          const bool v = scr.on[mm] != 0;
+          const float o = part[(2 * which) * kTileM + mm] + part[(2 * which + 1) * kTileM + mm] + __ldg(b2cat + which);
+          if (which == 0) sigma[i] = v ? density_act(o, cfg.act, cfg.density_shift) : 0.f;
+          else blend[i] = v ? sigmoidf_(o) : 0.f;
+        }
+      }
+      prod_bar();
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(ring.tmem, 128);
+}
+
+// reference column of density/blending layer-1 for (chunk j, row k) of the K order above
+__device__ __forceinline__ int sb_src_col(int j, int k) {
+  if (j >= 3) return ((j - 3) >> 1) * 24 + k;  // features: stride-major, reference order
+  const int r = j * 32 + k;                    // position/time row 0..79
+  const int q = r >> 2, e = r & 3;
+  int p;                                       // index in the reference's [xn3, sin30, cos30, t, tsin8, tcos8]
+  if (q == 0) p = e < 3 ? e : 63;
+  else if (q >= 16) {
+    const int tq = q - 16;
+    p = (tq < 2 ? 64 : 72) + (tq & 1) * 4 + e;
+  } else {
+    const int d = (q - 1) / 5, w = (q - 1) % 5;
+    if (w == 4) p = (e < 2 ? 3 : 33) + d * 10 + 8 + (e & 1);
+    else p = ((w & 1) ? 33 : 3) + d * 10 + (w >> 1) * 4 + e;
+  }
+  return 72 + p;
+}
+
+__global__ void k_pack_sb_umma(const float* __restrict__ w_den /*[64][152]*/, const float* __restrict__ w_bl, float* __restrict__ wq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kSbWFloats / 2) return;
+  // locate chunk
+  int j = 0, base = 0;
+  for (; j < kSbChunks; ++j) {
+    const int sz = sb_n(j) * sb_rows(j);
+    if (i < base + sz) break;
+    base += sz;
+  }
+  const int N = sb_n(j), rows = sb_rows(j);
+  const int e = i - base;
+  const int n = e / rows, k = e % rows;
+  const int col = sb_src_col(j, k);
+  float v;
+  if (j < 3) v = n < 64 ? __ldg(w_den + (size_t)n * 152 + col) : __ldg(w_bl + (size_t)(n - 64) * 152 + col);
+  else v = ((j - 3) & 1) ? __ldg(w_bl + (size_t)n * 152 + col) : __ldg(w_den + (size_t)n * 152 + col);
+  float hi, lo;
+  umma::split_tf32(v, hi, lo);
+  const uint32_t off = umma::kmajor_off(n, k, N) >> 2;
+  float* blob = wq + sb_woff(j);
+  blob[off] = hi;
+  blob[N * rows + off] = lo;
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight packing for the UMMA path: nn.Linear weight [N][K] -> chunks of 32 input columns,
 // each chunk = [hi: Npad x 32 K-major][lo: Npad x 32 K-major]; bias -> [Npad]
@@ -373,6 +763,39 @@ int dynrf_pack_linear_umma(const float* w, const float* bias, int N, int K, floa
   const int Npad = (N + 7) & ~7, nchunks = (K + kKC - 1) / kKC;
   const int total = nchunks * Npad * kKC;
   k_pack_linear_umma<<<(total + 255) / 256, 256, 0, S_(stream)>>>(w, bias, N, K, Npad, nchunks, wq, bias_out);
+  DYNRF_CHECK_LAUNCH();
+  return 0;
+}
+
+int dynrf_sb_umma_floats(void) { return kSbWFloats; }
+
+int dynrf_pack_sb_umma(const float* w_den, const float* w_bl, float* wq, void* stream) {
+  if (!w_den || !w_bl || !wq) return DYNRF_E_ARG;
+  k_pack_sb_umma<<<(kSbWFloats / 2 + 255) / 256, 256, 0, S_(stream)>>>(w_den, w_bl, wq);
+  DYNRF_CHECK_LAUNCH();
+  return 0;
+}
+
+int dynrf_dyn_sigma_blend_fwd_tc2(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density, const dynrf_vm_t* blending,
+                                  const float* wq, const float* b1cat, const float* w2cat, const float* b2cat, const float* xyz,
+                                  const float* xyz_prime, const uint8_t* valid, const float* tfeat, int N, int S, float* sigma,
+                                  float* blend, void* stream) {
+  if (!cfg || !density || !blending || !wq || !b1cat || !w2cat || !b2cat || !xyz || !xyz_prime || !valid || !tfeat || !sigma || !blend ||
+      N <= 0 || S <= 0)
+    return DYNRF_E_ARG;
+  for (int i = 0; i < 3; ++i) {
+    const int c = i == 0 ? 16 : 4;
+    if (density->C[i] != c || blending->C[i] != c) return DYNRF_E_UNSUPPORTED;
+  }
+  for (int i = 0; i < 3; ++i)
+    if (density->H[i] != blending->H[i] || density->W[i] != blending->W[i] || density->L[i] != blending->L[i]) return DYNRF_E_UNSUPPORTED;
+  if (((uintptr_t)wq & 15)) return DYNRF_E_ALIGN;
+  cudaError_t e = cudaFuncSetAttribute(k_dyn_sigma_blend_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSb2Smem);
+  if (e != cudaSuccess) return (int)e;
+  const int P = N * S;
+  const int grid = min((P + kTileM - 1) / kTileM, sm_count());
+  k_dyn_sigma_blend_tc2<<<grid, kTc3Threads, kSb2Smem, S_(stream)>>>(*cfg, *density, *blending, wq, b1cat, w2cat, b2cat, xyz,
+                                                                  xyz_prime, valid, tfeat, P, S, sigma, blend);
   DYNRF_CHECK_LAUNCH();
   return 0;
 }

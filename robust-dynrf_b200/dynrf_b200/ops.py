@@ -55,7 +55,26 @@ def to_channel_last_(p: torch.Tensor) -> None:
             p.data = p.data.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
 
 
+_VM_CACHE: Dict[tuple, "L.VmT"] = {}
+
+
 def vm_struct(planes: Sequence[torch.Tensor], lines: Sequence[torch.Tensor]) -> L.VmT:
+    """dynrf_vm_t for a plane/line set; cached on (data_ptr, shape) of the six tensors (pointers only change when a
+    parameter is replaced, e.g. by upsample_volume_grid; values may change in place)."""
+    key = tuple((t.data_ptr(), t.shape[2], t.shape[3], t.stride(1)) for t in (*planes, *lines))
+    hit = _VM_CACHE.get(key)
+    if hit is not None:
+        return hit
+    if len(_VM_CACHE) > 256:
+        _VM_CACHE.clear()
+    vm = _vm_struct_build(planes, lines)
+    # re-key after a possible in-place layout conversion moved the storage
+    key = tuple((t.data_ptr(), t.shape[2], t.shape[3], t.stride(1)) for t in (*planes, *lines))
+    _VM_CACHE[key] = vm
+    return vm
+
+
+def _vm_struct_build(planes: Sequence[torch.Tensor], lines: Sequence[torch.Tensor]) -> L.VmT:
     vm = L.VmT()
     for i in range(3):
         to_channel_last_(planes[i])
@@ -135,6 +154,7 @@ class PackedUmmaLayer:
 # tensor-core (tcgen05) kernels for the MLP stages that have them; the SIMT fp32 kernels stay in the library
 # as a cross-check (tests flip this flag to compare the two)
 USE_TC = True
+TC_SB_VERSION = 2
 
 
 def umma_layers(m, names):
@@ -148,6 +168,34 @@ def umma_layers(m, names):
             pl = cache[n] = PackedUmmaLayer(lin.weight, lin.bias)
         out[n] = pl.refresh()
     return out
+
+
+class PackedSigmaBlend:
+    """Operands of dynrf_dyn_sigma_blend_fwd_tc2, rebuilt when any of the four density / blending layers changes."""
+
+    def __init__(self, m):
+        self.m = m
+        dev = m.density_layer1.weight.device
+        self.wq = torch.empty(L.load().dynrf_sb_umma_floats(), device=dev)
+        self.b1cat = torch.empty(128, device=dev)
+        self.w2cat = torch.empty(128, device=dev)
+        self.b2cat = torch.empty(2, device=dev)
+        self._key = None
+
+    def refresh(self):
+        m = self.m
+        ps = [m.density_layer1.weight, m.density_layer1.bias, m.density_layer2.weight, m.density_layer2.bias,
+              m.blending_layer1.weight, m.blending_layer1.bias, m.blending_layer2.weight, m.blending_layer2.bias]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self._key:
+            with torch.no_grad():
+                wd, wb = _f32c(ps[0].detach()), _f32c(ps[4].detach())
+                L.check(L.load().dynrf_pack_sb_umma(_p(wd), _p(wb), _p(self.wq), _stream()), "dynrf_pack_sb_umma")
+                torch.cat((ps[1].detach(), ps[5].detach()), out=self.b1cat)
+                torch.cat((ps[2].detach().reshape(-1), ps[6].detach().reshape(-1)), out=self.w2cat)
+                torch.cat((ps[3].detach().reshape(-1), ps[7].detach().reshape(-1)), out=self.b2cat)
+            self._key = key
+        return self
 
 
 def field_cfg(aabb: torch.Tensor, near_far, distance_scale, weight_thres, act: str, density_shift, ray_type: str) -> L.FieldCfgT:
@@ -267,9 +315,20 @@ def dynamic_forward_raw(m, rays, ts, xyz, z_vals, valid, ray_type):
         ul = umma_layers(m, ("layer3", "layer4", "d1", "b1"))
         L.check(lib.dynrf_warp_fwd_tc(C.byref(cfg), _p(xyz), n, s, _p(tfeat), C.byref(ul["layer3"]), C.byref(ul["layer4"]),
                                       C.byref(ly["layer5"]), _p(xyz_prime), _stream()), "dynrf_warp_fwd_tc")
-        L.check(lib.dynrf_dyn_sigma_blend_fwd_tc(C.byref(cfg), C.byref(vden), C.byref(vbl), C.byref(ul["d1"]), C.byref(ly["d2"]),
-                                                 C.byref(ul["b1"]), C.byref(ly["b2"]), _p(xyz), _p(xyz_prime), _p(valid_u8),
-                                                 _p(tfeat), n, s, _p(sigma), _p(blend), _stream()), "dynrf_dyn_sigma_blend_fwd_tc")
+        if TC_SB_VERSION == 2:
+            psb = m.__dict__.get("_packed_sb")
+            if psb is None:
+                psb = m.__dict__["_packed_sb"] = PackedSigmaBlend(m)
+            psb.refresh()
+            L.check(lib.dynrf_dyn_sigma_blend_fwd_tc2(C.byref(cfg), C.byref(vden), C.byref(vbl), _p(psb.wq), _p(psb.b1cat),
+                                                      _p(psb.w2cat), _p(psb.b2cat), _p(xyz), _p(xyz_prime), _p(valid_u8),
+                                                      _p(tfeat), n, s, _p(sigma), _p(blend), _stream()),
+                    "dynrf_dyn_sigma_blend_fwd_tc2")
+        else:
+            L.check(lib.dynrf_dyn_sigma_blend_fwd_tc(C.byref(cfg), C.byref(vden), C.byref(vbl), C.byref(ul["d1"]),
+                                                     C.byref(ly["d2"]), C.byref(ul["b1"]), C.byref(ly["b2"]), _p(xyz),
+                                                     _p(xyz_prime), _p(valid_u8), _p(tfeat), n, s, _p(sigma), _p(blend),
+                                                     _stream()), "dynrf_dyn_sigma_blend_fwd_tc")
     else:
         L.check(lib.dynrf_warp_fwd(C.byref(cfg), _p(xyz), n, s, _p(tfeat), C.byref(ly["layer3"]), C.byref(ly["layer4"]),
                                    C.byref(ly["layer5"]), _p(xyz_prime), _stream()), "dynrf_warp_fwd")

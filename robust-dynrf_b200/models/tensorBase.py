@@ -168,12 +168,20 @@ class TensorBase(nn.Module):
         return {"basis": self.basis_mat, "h1": rm.mlp[0], "h2": rm.mlp[2], "h3": last}
 
     def packed_layers(self):
+        """name -> dynrf_layer_t, repacked only when a parameter changed.  One cheap key over all layers
+        (data_ptr + in-place version counter) guards the whole table so the steady state costs ~20 us."""
+        tbl = self._layer_table()
+        key = tuple((lin.weight.data_ptr(), lin.weight._version, -1 if lin.bias is None else lin.bias._version)
+                    for lin in tbl.values())
+        if getattr(self, "_packed_key", None) == key:
+            return self._packed_out
         out = {}
-        for name, lin in self._layer_table().items():
+        for name, lin in tbl.items():
             pl = self._packed.get(name)
             if pl is None or pl.weight is not lin.weight or pl.bias is not lin.bias:
                 pl = self._packed[name] = _ops.PackedLayer(lin.weight, lin.bias)
             out[name] = pl.refresh()
+        self._packed_key, self._packed_out = key, out
         return out
 
     # ------------------------------------------------------------------ small utilities kept for callers

@@ -63,6 +63,12 @@ def main():
     vden, vbl, vapp = ops.vm_struct(dyn.density_plane, dyn.density_line), ops.vm_struct(dyn.blending_plane, dyn.blending_line), ops.vm_struct(dyn.app_plane, dyn.app_line)
     res["dyn.sigma_blend"] = timeit(lambda: lib.dynrf_dyn_sigma_blend_fwd(C.byref(cfgd), C.byref(vden), C.byref(vbl), C.byref(ly["d1"]), C.byref(ly["d2"]), C.byref(ly["b1"]), C.byref(ly["b2"]), p(xyz), p(d["xyz_prime"]), p(d["valid"]), p(d["tfeat"]), n, s, p(d["sigma"]), p(d["blend"]), S_()))
     res["dyn.app"] = timeit(lambda: lib.dynrf_dyn_app_fwd(C.byref(cfgd), C.byref(vapp), C.byref(ly["basis"]), C.byref(ly["h1"]), C.byref(ly["h2"]), C.byref(ly["h3"]), p(rays), p(xyz), p(d["xyz_prime"]), p(d["tfeat"]), n, s, p(d["idx"]), p(d["cnt"]), p(d["rgb"]), S_()))
+    def dyn_only(tc, ver=2):
+        ops.USE_TC, ops.TC_SB_VERSION = tc, ver
+        return timeit(lambda: ops.dynamic_forward_raw(dyn, rays, ts, xyz, z, valid, rt))
+    res["dynamic_forward(simt)"] = dyn_only(False)
+    res["dynamic_forward(tc v1)"] = dyn_only(True, 1)
+    res["dynamic_forward(tc v2)"] = dyn_only(True, 2)
     res["composite"] = timeit(lambda: ops.composite_raw(st["rgb"], st["sigma"], d["rgb"], d["sigma"], d["dists"], d["blend"], z, rays, False, rt))
     ns = a.rays * a.samples
     t_gen = res["static_sigma_weight(generated)"][1]
