@@ -154,7 +154,10 @@ int dynrf_dyn_sigma_blend_fwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* de
 int dynrf_dyn_app_fwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* app, const dynrf_layer_t* basis,
                       const dynrf_layer_t* l1, const dynrf_layer_t* l2, const dynrf_layer_t* l3, const float* rays,
                       const float* xyz, const float* xyz_prime, const float* tfeat, int N, int S,
-                      const int32_t* active_idx, const int32_t* active_count, float* rgb, void* stream);
+                      const int32_t* active_idx, const int32_t* active_count, float* rgb, float* featT_or_null, int ldf,
+                      void* stream);
+/* featT [32][ldf] (optional): the 27 basis outputs of active sample j at column j, feature-major, rows 27..31 zero;
+ * consumed by dynrf_dyn_head_bwd_tc.  ldf >= round_up(N*S, 128). */
 
 /* ---- a19: two-field compositing (renderer.raw2outputs, renderer.py:173-315) ----------------
  * white_bg: the reference's host-side coin (is_train && rand<0.5), decided by the caller.
@@ -259,6 +262,24 @@ int dynrf_dyn_sigma_blend_fwd_tc2(const dynrf_field_cfg_t* cfg, const dynrf_vm_t
                                   const float* wq, const float* b1cat, const float* w2cat, const float* b2cat,
                                   const float* xyz, const float* xyz_prime, const uint8_t* valid, const float* tfeat, int N,
                                   int S, float* sigma, float* blend, void* stream);
+
+/* ---- tensor-core backward of the dynamic appearance head (late-view MLP on the active samples) -----------
+ * dynrf_pack_head_bwd: layer-1 [128][107] / layer-2 [128][128] weights -> dynrf_head_bwd_wfloats() packed floats + the column
+ *   map [113] of X1T rows to nn.Linear input columns (-1: padding row, -2: the ones row whose gradient column is d bias).
+ * dynrf_dyn_head_bwd_tc: cst = [b1(128) | b2(128) | W3[:, :128]^T (128x3) | W3[:, 128:131]^T (3x3) | b3(3)];
+ *   writes feature-major [rows][ld] tensors X1T[113] H1T[128] H2T[128] DH2T[128] DH1T[128] DOT[3] DFT[32] (column j = j-th
+ *   active sample) and accumulates gw3v [3][3] (d W3[:, 128+k]) and gb3 [3].  ld >= round_up(N*S,128), multiple of 4.
+ * dynrf_basis_bwd: DFT -> packed basis gradient [K][32] (+=), plane / line gradients (+=), d loss / d coords (+=). */
+int dynrf_head_bwd_wfloats(void);
+int dynrf_head_bwd_cst_floats(void);
+int dynrf_pack_head_bwd(const float* w1, const float* w2, float* wq, int32_t* colmap, void* stream);
+int dynrf_dyn_head_bwd_tc(const dynrf_field_cfg_t* cfg, const float* wq, const float* cst, const float* rays, const float* xyz,
+                          const float* tfeat, const float* featT, const float* grgb, const int32_t* active_idx,
+                          const int32_t* active_count, int N, int S, int ld, float* X1T, float* H1T, float* H2T, float* DH2T,
+                          float* DH1T, float* DOT, float* DFT, float* gw3v, float* gb3, void* stream);
+int dynrf_basis_bwd(const dynrf_field_cfg_t* cfg, int dynamic, const dynrf_vm_t* app, const dynrf_vm_grad_t* gapp, const float* wbB,
+                    const float* coords, const float* DFT, int ld, int N, int S, const int32_t* active_idx,
+                    const int32_t* active_count, float* gbasis_wt, float* gcoord, void* stream);
 
 /* Weight-gradient GEMM on tensor cores (3-pass split TF32, fp32 TMEM accumulation):
  *   dw[n * dw_ld + k] += sum_{p < P} XT[k * ldx + p] * DYT[n * ldy + p],  k < K <= 256, n < N <= 128,

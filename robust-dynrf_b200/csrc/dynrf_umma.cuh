@@ -117,5 +117,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
   for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
 }
 
+// 16-column variant
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+  uint32_t u[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+        "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+}
+
 }  // namespace umma
 }  // namespace dynrf

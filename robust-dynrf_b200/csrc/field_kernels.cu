@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kMlpThreads)
 k_dyn_app(dynrf_field_cfg_t cfg, dynrf_vm_t vapp, dynrf_layer_t basis, dynrf_layer_t l1, dynrf_layer_t l2, dynrf_layer_t l3,
           const float* __restrict__ rays, const float* __restrict__ xyz, const float* __restrict__ xyz_prime,
           const float* __restrict__ tfeat, int S, const int32_t* __restrict__ active_idx, const int32_t* __restrict__ active_count,
-          float* __restrict__ rgb) {
+          float* __restrict__ rgb, float* __restrict__ featT, int ldf) {
   extern __shared__ __align__(16) float smem[];
   float* Ac = smem;
   float* X = Ac + 72 * kTileM;
@@ -230,6 +230,12 @@ k_dyn_app(dynrf_field_cfg_t cfg, dynrf_vm_t vapp, dynrf_layer_t basis, dynrf_lay
       acc_gemm<32, kTileM, kTileM>(fa, Ac, 72, basis.wt + (size_t)si * 72 * 32, wbuf, tid);
     }
     acc_store<32, kTileM, kTileM, false>(fa, X, 27, tid);
+    if (featT) {  // basis output, feature-major, for the tensor-core backward
+      for (int item = tid; item < 32 * kTileM; item += kMlpThreads) {
+        const int mm = item & (kTileM - 1), k = item >> 7;
+        featT[(size_t)k * ldf + tile * kTileM + mm] = (k < 27 && scr.on[mm]) ? X[(size_t)k * kTileM + mm] : 0.f;
+      }
+    }
     dense_tile<128, kTileM, kTileM, true>(X, l1, H1, wbuf, tid);
     dense_tile<128, kTileM, kTileM, true>(H1, l2, H2, wbuf, tid);
     if (tid < kTileM) {
@@ -457,8 +463,9 @@ int dynrf_dyn_sigma_blend_fwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* de
 int dynrf_dyn_app_fwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* app, const dynrf_layer_t* basis, const dynrf_layer_t* l1,
                       const dynrf_layer_t* l2, const dynrf_layer_t* l3, const float* rays, const float* xyz,
                       const float* xyz_prime, const float* tfeat, int N, int S, const int32_t* active_idx,
-                      const int32_t* active_count, float* rgb, void* stream) {
+                      const int32_t* active_count, float* rgb, float* featT, int ldf, void* stream) {
   if (!cfg || !rays || !xyz || !xyz_prime || !tfeat || !active_idx || !active_count || !rgb || N <= 0 || S <= 0) return DYNRF_E_ARG;
+  if (featT && ldf < ((N * S + kTileM - 1) / kTileM) * kTileM) return DYNRF_E_ARG;
   DYNRF_TRY(check_vm_counts(app, 48, 12, 12));
   DYNRF_TRY(check_layer(basis, 216, 27, 32));
   DYNRF_TRY(check_layer(l1, 107, 128, 128));
@@ -468,7 +475,7 @@ int dynrf_dyn_app_fwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* app, const
   const int ntiles = (N * S + kTileM - 1) / kTileM;
   const int grid = min(ntiles, sm_count());
   k_dyn_app<<<grid, kMlpThreads, kDaSmem, S_(stream)>>>(*cfg, *app, *basis, *l1, *l2, *l3, rays, xyz, xyz_prime, tfeat, S, active_idx,
-                                                        active_count, rgb);
+                                                        active_count, rgb, featT, ldf);
   DYNRF_CHECK_LAUNCH();
   return 0;
 }

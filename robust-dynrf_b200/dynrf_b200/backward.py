@@ -191,7 +191,8 @@ _DYN_LAYER_ORDER = ["basis", "h1", "h2", "h3", "layer1", "layer2", "layer3", "la
 class DynamicFieldFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, ray_type, rays, ts, xyz, z_vals, valid, *params):
-        r = ops.dynamic_forward_raw(model, rays.detach(), ts.detach(), xyz.detach(), z_vals.detach(), valid, ray_type)
+        r = ops.dynamic_forward_raw(model, rays.detach(), ts.detach(), xyz.detach(), z_vals.detach(), valid, ray_type,
+                                    save_feat=ops.USE_TC)
         ctx.model, ctx.ray_type, ctx.r = model, ray_type, r
         ctx.set_materialize_grads(False)
         return r["blend"], r["weight"], r["xyz_prime"], r["rgb"], r["sigma"], r["dists"]
@@ -215,7 +216,10 @@ class DynamicFieldFn(torch.autograd.Function):
         gbl_p, gbl_l, gbl = _vm_grads(m.blending_plane, m.blending_line)
         gden_p, gden_l, gden = _vm_grads(m.density_plane, m.density_line)
         gapp_p, gapp_l, gapp = _vm_grads(m.app_plane, m.app_line)
-        if grgb is not None:
+        tc_head = None
+        if grgb is not None and ops.USE_TC and r.get("featT") is not None:
+            tc_head = _dyn_head_bwd_tc(m, cfg, r, _f32c(grgb), gl, gapp, gxp, n, s)
+        elif grgb is not None:
             vapp = ops.vm_struct(m.app_plane, m.app_line)
             wb2 = pack_bwd(pk["h2"], 0, 128, 128)
             wb1f = pack_bwd(pk["h1"], 0, 27, 128)
@@ -248,11 +252,95 @@ class DynamicFieldFn(torch.autograd.Function):
         grays = _rays_grad_from(r["rays"], r["z_vals"], float(m.distance_scale), gd, None) if ctx.needs_input_grad[2] else None
         pg = gbl_p + gbl_l + gden_p + gden_l + gapp_p + gapp_l
         for k in _DYN_LAYER_ORDER:
-            dw, db = gl[k].unpack()
+            if tc_head is not None and k in tc_head:
+                dw, db = tc_head[k]
+            else:
+                dw, db = gl[k].unpack()
             pg.append(dw)
             if db is not None:
                 pg.append(db)
         return (None, None, grays, None, None, None, None, *pg)
+
+
+class _HeadBwdState:
+    """Per-model packed weights / constants / scratch of the tensor-core head backward."""
+
+    def __init__(self, m):
+        lib = L.load()
+        dev = m.basis_mat.weight.device
+        self.wq = torch.empty(lib.dynrf_head_bwd_wfloats(), device=dev)
+        self.cst = torch.empty(lib.dynrf_head_bwd_cst_floats(), device=dev)
+        self.colmap = torch.empty(113, dtype=torch.int32, device=dev)
+        self.key = None
+        self.bufs = {}
+
+    def refresh(self, m):
+        rm = m.renderModule
+        l1, l2, l3 = rm.mlp[0], rm.mlp[2], rm.mlp_view[0]
+        key = tuple((p.data_ptr(), p._version) for p in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias))
+        if key != self.key:
+            with torch.no_grad():
+                L.check(L.load().dynrf_pack_head_bwd(_p(_f32c(l1.weight.detach())), _p(_f32c(l2.weight.detach())), _p(self.wq),
+                                                     _p(self.colmap), _stream()), "dynrf_pack_head_bwd")
+                w3 = l3.weight.detach()
+                torch.cat((l1.bias.detach(), l2.bias.detach(), w3[:, :128].t().reshape(-1), w3[:, 128:131].t().reshape(-1),
+                           l3.bias.detach()), out=self.cst)
+                cm = self.colmap.long()
+                self.src_rows = torch.nonzero(cm >= 0).reshape(-1)     # X1T rows that map to a layer-1 input column
+                self.dst_cols = cm[self.src_rows]
+            self.key = key
+        return self
+
+    def scratch(self, ld, dev):
+        b = self.bufs.get(ld)
+        if b is None:
+            b = self.bufs[ld] = dict(X1T=torch.empty(113, ld, device=dev), H1T=torch.empty(128, ld, device=dev),
+                                     H2T=torch.empty(128, ld, device=dev), DH2T=torch.empty(128, ld, device=dev),
+                                     DH1T=torch.empty(128, ld, device=dev), DOT=torch.empty(4, ld, device=dev),
+                                     DFT=torch.empty(32, ld, device=dev))
+        return b
+
+
+def _wgrad(XT, K, DYT, N, ld, cnt, out, out_ld):
+    L.check(L.load().dynrf_wgrad_gemm(_p(XT), ld, K, _p(DYT), ld, N, ld, _p(cnt), _p(out), out_ld, _stream()), "dynrf_wgrad_gemm")
+
+
+def _dyn_head_bwd_tc(m, cfg, r, grgb, gl, gapp, gxp, n, s):
+    """Tensor-core appearance-head backward: fused tile kernel (recompute + data gradients) -> wgrad GEMMs -> basis / lookups."""
+    lib = L.load()
+    st = m.__dict__.get("_head_bwd_state")
+    if st is None:
+        st = m.__dict__["_head_bwd_state"] = _HeadBwdState(m)
+    st.refresh(m)
+    dev = grgb.device
+    ld = r["ldf"]
+    b = st.scratch(ld, dev)
+    gw3v = torch.zeros(3, 3, device=dev)
+    gb3 = torch.zeros(3, device=dev)
+    L.check(lib.dynrf_dyn_head_bwd_tc(C.byref(cfg), _p(st.wq), _p(st.cst), _p(r["rays"]), _p(r["xyz"]), _p(r["tfeat"]), _p(r["featT"]),
+                                      _p(grgb), _p(r["idx"]), _p(r["cnt"]), n, s, ld, _p(b["X1T"]), _p(b["H1T"]), _p(b["H2T"]),
+                                      _p(b["DH2T"]), _p(b["DH1T"]), _p(b["DOT"]), _p(b["DFT"]), _p(gw3v), _p(gb3), _stream()),
+            "dynrf_dyn_head_bwd_tc")
+    cnt = r["cnt"]
+    dw1m = torch.zeros(128, 113, device=dev)
+    _wgrad(b["X1T"], 113, b["DH1T"], 128, ld, cnt, dw1m, 113)
+    dw1 = torch.zeros(128, 107, device=dev)
+    dw1[:, st.dst_cols] = dw1m[:, st.src_rows]
+    db1 = dw1m[:, 112].contiguous()
+    dw2 = torch.zeros(128, 128, device=dev)
+    _wgrad(b["H1T"], 128, b["DH2T"], 128, ld, cnt, dw2, 128)
+    db2 = torch.zeros(128, 1, device=dev)
+    _wgrad(b["X1T"][112:113], 1, b["DH2T"], 128, ld, cnt, db2, 1)   # ones row -> column sums
+    dw3 = torch.zeros(3, 131, device=dev)
+    _wgrad(b["H2T"], 128, b["DOT"], 3, ld, cnt, dw3, 131)
+    dw3[:, 128:131] = gw3v
+    # basis_mat + lookups (SIMT tile kernel)
+    pk = m._packed
+    vapp = ops.vm_struct(m.app_plane, m.app_line)
+    wbB = torch.cat([pack_bwd(pk["basis"], 72 * i, 72 * i + 72, 32) for i in range(3)])
+    L.check(lib.dynrf_basis_bwd(C.byref(cfg), 1, C.byref(vapp), C.byref(gapp), _p(wbB), _p(r["xyz_prime"]), _p(b["DFT"]), ld, n, s,
+                                _p(r["idx"]), _p(cnt), _p(gl["basis"].dwt), _p(gxp), _stream()), "dynrf_basis_bwd")
+    return {"h1": (dw1, db1), "h2": (dw2, db2.reshape(-1)), "h3": (dw3, gb3)}
 
 
 def field_forward_with_grad(model, rays, ts, xyz, z_vals, valid, ray_type):

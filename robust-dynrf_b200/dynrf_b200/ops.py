@@ -294,7 +294,11 @@ def static_app_raw(m, st, ray_type):
             "dynrf_static_app_fwd")
 
 
-def dynamic_forward_raw(m, rays, ts, xyz, z_vals, valid, ray_type):
+def round_up(x, k):
+    return (x + k - 1) // k * k
+
+
+def dynamic_forward_raw(m, rays, ts, xyz, z_vals, valid, ray_type, save_feat=False):
     lib = L.load()
     _require_cuda(rays, ts, xyz)
     rays, ts, xyz, z_vals = _f32c(rays), _f32c(ts), _f32c(xyz), _f32c(z_vals)
@@ -342,11 +346,13 @@ def dynamic_forward_raw(m, rays, ts, xyz, z_vals, valid, ray_type):
     L.check(lib.dynrf_alpha_weight_fwd(C.byref(cfg), _p(rays), n, s, _p(sigma), _p(z_vals), _p(weight), _p(dists), _p(idx),
                                        _p(cnt), _p(rgb), _stream()), "dynrf_alpha_weight_fwd")
     vapp = vm_struct(m.app_plane, m.app_line)
+    ldf = round_up(n * s, 128)
+    featT = torch.empty(32, ldf, device=dev) if save_feat else None  # basis outputs, kept for the tensor-core backward
     L.check(lib.dynrf_dyn_app_fwd(C.byref(cfg), C.byref(vapp), C.byref(ly["basis"]), C.byref(ly["h1"]), C.byref(ly["h2"]),
                                   C.byref(ly["h3"]), _p(rays), _p(xyz), _p(xyz_prime), _p(tfeat), n, s, _p(idx), _p(cnt),
-                                  _p(rgb), _stream()), "dynrf_dyn_app_fwd")
+                                  _p(rgb), _p(featT), ldf, _stream()), "dynrf_dyn_app_fwd")
     return dict(sigma=sigma, blend=blend, weight=weight, dists=dists, rgb=rgb, xyz_prime=xyz_prime, tfeat=tfeat, idx=idx,
-                cnt=cnt, rays=rays, ts=ts, xyz=xyz, z_vals=z_vals, valid=valid_u8)
+                cnt=cnt, rays=rays, ts=ts, xyz=xyz, z_vals=z_vals, valid=valid_u8, featT=featT, ldf=ldf)
 
 
 def composite_raw(rgb_s, sigma_s, rgb_d, sigma_d, dists, blending, z_vals, rays, white_bg: bool, ray_type: str):
