@@ -61,7 +61,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250",
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -94,44 +94,74 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------- reference arm (CPU)
 
 
-def cpu_reference(n_rays, reps, warm=1, seed=1):
-    """The reference's CPU path (oracle port, torch fp32, all host threads) on a bounded sample of the workload."""
-    from tests import helpers as H
+class CpuReference:
+    """The reference's CPU path (oracle port, torch fp32 on all host threads) on a bounded sample of the workload.
 
-    case = H.build_pair(GRID, n_rays, N_SAMPLES, ray_type="ndc", seed=seed)
-    for _ in range(warm):
-        H.oracle_pass(case)
-    ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        H.oracle_pass(case)
-        ts.append(time.perf_counter() - t0)
-    return n_rays / min(ts), n_rays / (sum(ts) / len(ts)), ts
+    mode "fwd": sampleXYZ -> both fields -> raw2outputs under no_grad.  mode "train": the same pass with autograd, the
+    3-term MSE loss of the native arm, loss.backward() and an Adam update of every parameter (train.py:1092-1162)."""
+
+    def __init__(self, n_rays, mode, seed=1):
+        from tests import helpers as H
+        from oracle import rodynrf_oracle as O
+
+        self.H, self.O, self.n, self.mode = H, O, n_rays, mode
+        self.case = H.build_pair(GRID, n_rays, N_SAMPLES, ray_type="ndc", seed=seed)
+        if mode == "train":
+            c = self.case
+            self.ss = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in c["sd_static"].items()}
+            self.sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in c["sd_dynamic"].items()}
+            params = [v for v in list(self.ss.values()) + list(self.sd.values()) if v.requires_grad]
+            self.opt = torch.optim.Adam(params, lr=1e-4, betas=(0.9, 0.99))
+            self.target = torch.rand(n_rays, 3, generator=torch.Generator().manual_seed(5))
+
+    def step(self):
+        if self.mode != "train":
+            self.H.oracle_pass(self.case)
+            return
+        O, c = self.O, self.case
+        xyz, z, valid = O.sampleXYZ(c["cd"], c["rays"], c["n_samples"], c["ray_type"], True)
+        fs = O.field_forward(c["cs"], self.ss, c["rays"], c["ts"], xyz, z, valid, c["ray_type"])
+        fd = O.field_forward(c["cd"], self.sd, c["rays"], c["ts"], xyz, z, valid, c["ray_type"])
+        o = O.raw2outputs(fs[6], fs[7], fd[6], fd[7], fd[9], fd[2], fd[8], c["rays"], False, c["ray_type"])
+        t = self.target
+        loss = ((o[0] - t) ** 2).mean() + ((o[4] - t) ** 2).mean() + ((o[8] - t) ** 2).mean()
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self.opt.step()
+
+    def time(self, reps, warm):
+        for _ in range(warm):
+            self.step()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            self.step()
+            ts.append(time.perf_counter() - t0)
+        return ts
+
+    def describe(self, ts):
+        what = "forward + backward + Adam" if self.mode == "train" else "forward pass"
+        return (f"{self.n} rays x {N_SAMPLES} samples per step at the full grid {GRID}, {what}, torch fp32 CPU oracle port "
+                f"({sum(ts):.1f} s of CPU work)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = 512
+    mode = "train" if args.mode in ("auto", "train") else "fwd"
+    n = 1024
     cores = torch.get_num_threads()
-    from tests import helpers as H
-
-    case = H.build_pair(GRID, n, N_SAMPLES, ray_type="ndc", seed=1)
-    for _ in range(args.warmup):
-        H.oracle_pass(case)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        H.oracle_pass(case)
-    dt = time.perf_counter() - t0
+    ref = CpuReference(n, mode)
+    ts = ref.time(args.steps, args.warmup)
+    dt = sum(ts)
     v = n * args.steps / dt
-    sample = f"{n} rays x {N_SAMPLES} samples per step at the full grid {GRID} (forward pass, torch fp32 CPU)"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "mode": "fwd", "note": "reference CPU implementation of the path (oracle port of the reference's PyTorch code)"},
-        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "mode": mode, "note": "reference CPU implementation of the path (oracle port of the reference's PyTorch code)"},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": ref.describe(ts)},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -147,6 +177,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--mode", default="auto", choices=["auto", "fwd", "train"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":
@@ -184,7 +215,7 @@ def main():
     rays_d, ts_d, target_d = rays_h.to(dev), ts_h.to(dev), target_h.to(dev)
     out_pin = torch.empty(N_RAYS, 16, pin_memory=True)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    step = TS.Step(static, dyn, N_SAMPLES, "ndc", mode, world)
+    step = TS.Step(static, dyn, N_SAMPLES, "ndc", mode, world, graph=not args.no_graph)
 
     def one(rays, ts, target, fused=True):
         return step(rays, ts, target, fused=fused)
@@ -200,9 +231,7 @@ def main():
     barrier()
 
     # ---- device-resident timing
-    L.profile_events = {"dynrf_static_sigma_weight_fwd": [], "dynrf_dyn_sigma_blend_fwd": []}
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches0 = L.launch_count
     barrier()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)
@@ -210,11 +239,8 @@ def main():
         one(rays_d, ts_d, target_d)
         ev[i][1].record()
     barrier()
-    launches = L.launch_count - launches0
+    launches = step.launches_per_step * args.steps  # counted per eager step; a graph replay launches the same kernels
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
-    k1 = [a.elapsed_time(b) for a, b in L.profile_events["dynrf_static_sigma_weight_fwd"]]
-    ksb = [a.elapsed_time(b) for a, b in L.profile_events["dynrf_dyn_sigma_blend_fwd"]]
-    L.profile_events = None
     clocks = sampler.stop() if sampler else None
 
     # ---- end-to-end: pinned host -> device -> step -> host
@@ -233,6 +259,20 @@ def main():
         ev2[i][1].record()
     barrier()
     t2_ms = sum(a.elapsed_time(b) for a, b in ev2)
+
+    # ---- per-kernel times for the roofline lines: eager forward passes (the same forward kernels the train step runs),
+    # CUDA events around the two entry points on the launching stream, L2 flushed between passes
+    DOM = "dynrf_dyn_sigma_blend_fwd_tc2"
+    prof = TS.Step(static, dyn, N_SAMPLES, "ndc", "fwd", 1, graph=False)
+    prof.forward_fused(rays_d, ts_d)
+    L.profile_events = {"dynrf_static_sigma_weight_fwd": [], DOM: [], "dynrf_dyn_sigma_blend_fwd": []}
+    for i in range(max(5, min(args.steps, 20))):
+        flush.fill_(i & 0xFF)
+        prof.forward_fused(rays_d, ts_d)
+    torch.cuda.synchronize()
+    k1 = [a.elapsed_time(b) for a, b in L.profile_events["dynrf_static_sigma_weight_fwd"]]
+    ksb = [a.elapsed_time(b) for a, b in (L.profile_events[DOM] or L.profile_events["dynrf_dyn_sigma_blend_fwd"])]
+    L.profile_events = None
 
     tt = torch.tensor([t_ms, t2_ms], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -258,28 +298,29 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "mode": mode, "rays_per_gpu": N_RAYS, "samples_per_ray": N_SAMPLES,
                        "grid": GRID, "parallelism": f"rays sharded x{world}, parameters replicated",
+                       "cuda_graph": not args.no_graph,
                        "l2": "512 MiB buffer rewritten between timed iterations (L2 flush); parameters 93 MB + per-sample tensors"},
             "roofline": {"kernel": "k_static_sigma_weight (static density + sigma->alpha + transmittance scan, a6+a8+a9)",
                          "bound": "hbm", "achieved": k1_gbs, "peak": pk["hbm"], "unit": "GB/s",
                          "frac": (k1_gbs / pk["hbm"]) if k1_gbs else None, "traffic": traffic,
                          "ms_per_launch": k1_ms, "bytes_per_sample": BYTES_PER_SAMPLE_K1, "peak_source": pk["src"],
                          "note": "algorithmic bytes (every tap counted); the 10 MB density tables are L2-resident so DRAM traffic is far lower -- see profiles/"},
-            "roofline_dominant": {"kernel": "k_dyn_sigma_blend (a16+a17: 3-scale lookups + two 152->64->1 MLPs, fp32 FFMA)",
+            "roofline_tensor": {"kernel": "k_dyn_sigma_blend_tc2 (a16+a17: 3-scale lookups + two 152->64->1 MLPs, tcgen05 3-pass split-TF32)",
                                   "bound": "tensor", "achieved": sb_flops / (ksb_ms * 1e-3) / 1e12 if ksb else None,
                                   "peak": pk["tf_sust"], "unit": "TFLOP/s",
                                   "frac": (sb_flops / (ksb_ms * 1e-3) / 1e12 / pk["tf_sust"]) if ksb else None,
                                   "ms_per_launch": ksb_ms, "peak_source": pk["src"],
-                                  "note": "fp32 SIMT MLP engine; bf16 tensor peak quoted as the denominator the task names"},
+                                  "note": "useful fp32-equivalent flops (the tensor cores execute 3x this as TF32 passes); bf16 dense peak quoted as the denominator the task names"},
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": int(rays_pin.numel() * 4 + ts_pin.numel() * 4 + target_pin.numel() * 4),
                     "d2h_bytes_per_step": int(out_pin.numel() * 4), "ms_per_step": t2_ms / args.steps},
             "gpu_launches": launches, "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
             n_cpu = 1024
-            best, mean, tsamp = cpu_reference(n_cpu, reps=3, warm=1)
-            line["cpu_baseline"] = {"value": best, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"{n_cpu} rays x {N_SAMPLES} samples, full grid {GRID}, forward pass, best of 3 after 1 warm-up "
-                                              f"({sum(tsamp):.1f} s of CPU work)"}
+            ref = CpuReference(n_cpu, mode)
+            tsamp = ref.time(reps=3, warm=1)
+            line["cpu_baseline"] = {"value": n_cpu / min(tsamp), "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": ref.describe(tsamp) + ", best of 3 after 1 warm-up"}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -281,6 +281,23 @@ int dynrf_basis_bwd(const dynrf_field_cfg_t* cfg, int dynamic, const dynrf_vm_t*
                     const float* coords, const float* DFT, int ld, int N, int S, const int32_t* active_idx,
                     const int32_t* active_count, float* gbasis_wt, float* gcoord, void* stream);
 
+/* ---- tensor-core backward of the dynamic density + blending stage (reference: TensorBase.compute_densityfeature /
+ * blending MLP backward reached through loss.backward() from train.py; forward at models/tensorBase.py density_layer*,
+ * blending_layer*) -- both tables in one launch.
+ * dynrf_pack_sb_bwd: layer-1 weights [64][152] of the two MLPs -> dynrf_sb_bwd_wfloats() packed floats + colmap80 (row r of the
+ *   position/time block of XT -> nn.Linear input column).
+ * dynrf_dyn_mlp_bwd_tc: cst = [b1 density(64) | b1 blending(64) | w2 density(64) | w2 blending(64) | b2 density | b2 blending];
+ *   gsigma / gblend [N*S] (either may be NULL); writes XT [225][ld] (80 position/time rows in engine order, 72 density features,
+ *   72 blending features, ones row) and DHT [128][ld] (d pre-activation of layer 1, density | blending) for dynrf_wgrad_gemm;
+ *   accumulates plane / line gradients, gxp [N*S][3], gw2 [128], gb1 [128], gb2 [2].  ld >= round_up(N*S,128), multiple of 4. */
+int dynrf_sb_bwd_wfloats(void);
+int dynrf_pack_sb_bwd(const float* w1_density, const float* w1_blending, float* wq, int32_t* colmap80, void* stream);
+int dynrf_dyn_mlp_bwd_tc(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density, const dynrf_vm_t* blending,
+                         const dynrf_vm_grad_t* gdensity, const dynrf_vm_grad_t* gblending, const float* wq, const float* cst,
+                         const float* xyz, const float* xyz_prime, const uint8_t* valid, const float* tfeat, const float* gsigma,
+                         const float* gblend, int N, int S, int ld, float* XT, float* DHT, float* gxp, float* gw2, float* gb1,
+                         float* gb2, void* stream);
+
 /* Weight-gradient GEMM on tensor cores (3-pass split TF32, fp32 TMEM accumulation):
  *   dw[n * dw_ld + k] += sum_{p < P} XT[k * ldx + p] * DYT[n * ldy + p],  k < K <= 256, n < N <= 128,
  * P = min(*count_ptr, Pmax) (count_ptr may be NULL).  XT / DYT: feature-major activations / output gradients written by the

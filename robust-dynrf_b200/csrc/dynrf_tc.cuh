@@ -175,6 +175,33 @@ __device__ __forceinline__ void ring_issue(const Ring& r, int rows, uint32_t col
   umma::commit(&r.bar_free[c % 3]);
 }
 
+// row 0..79 of the position/time operand block (this engine's K order, see tc_kernels.cu) -> index 0..79 in the
+// reference's [xn(3), sin PE(30), cos PE(30), t, sin PE(t)(8), cos PE(t)(8)]
+__device__ __forceinline__ int pos_src_index(int r) {  // row 0..79 of the position/time block -> reference index 0..79
+  const int qd = r >> 2, e = r & 3;
+  if (qd == 0) return e < 3 ? e : 63;
+  if (qd >= 16) {
+    const int tq = qd - 16;
+    return (tq < 2 ? 64 : 72) + (tq & 1) * 4 + e;
+  }
+  const int d = (qd - 1) / 5, w = (qd - 1) % 5;
+  if (w == 4) return (e < 2 ? 3 : 33) + d * 10 + 8 + (e & 1);
+  return ((w & 1) ? 33 : 3) + d * 10 + (w >> 1) * 4 + e;
+}
+
+
+// backward tap: forward tap + validity + d(index)/d(coord)
+struct TapB {
+  int i0, i1;
+  float w0, w1;  // 1 - frac, frac (raw)
+  float scale;
+  bool v0, v1;
+};
+__device__ __forceinline__ TapB tapb(float x, int n, int s) {
+  const Tap1 t = make_tap(x, n, s);
+  return TapB{t.i0, t.i1, t.r0, t.r1, t.scale, t.v0, t.v1};
+}
+
 constexpr int kProdThreads = 512;
 constexpr int kTc3Threads = kProdThreads + 32;
 

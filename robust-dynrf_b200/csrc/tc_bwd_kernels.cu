@@ -333,18 +333,6 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
 //   j 8..11  dH1 = dH2 W2             : B[kin][nn] = W2[32 (j-8) + nn][kin]
 //   j 12..15 dfeat = dH1 W1[:, feat]  : B[f][nn] = W1[32 (j-12) + nn][f] (f < 27)
 
-__device__ __forceinline__ int pos_src_index(int r) {  // row 0..79 of the position/time block -> reference index 0..79
-  const int qd = r >> 2, e = r & 3;
-  if (qd == 0) return e < 3 ? e : 63;
-  if (qd >= 16) {
-    const int tq = qd - 16;
-    return (tq < 2 ? 64 : 72) + (tq & 1) * 4 + e;
-  }
-  const int d = (qd - 1) / 5, w = (qd - 1) % 5;
-  if (w == 4) return (e < 2 ? 3 : 33) + d * 10 + 8 + (e & 1);
-  return ((w & 1) ? 33 : 3) + d * 10 + (w >> 1) * 4 + e;
-}
-
 __global__ void k_pack_head_bwd(const float* __restrict__ w1 /*[128][107]*/, const float* __restrict__ w2 /*[128][128]*/,
                                 float* __restrict__ wq) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

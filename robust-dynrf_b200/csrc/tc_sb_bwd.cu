@@ -1,0 +1,437 @@
+// Tensor-core backward of the dynamic density + blending stage (a16 + a17), both tables in one launch.
+//
+// Per 128-sample tile (warp-specialised like k_dyn_sigma_blend_tc2): recompute layer 1 of both MLPs on tensor cores
+// (shared position/time rows against the concatenated weights, then the per-table 3-scale features), finish layer 2 and
+// the activations in the epilogue, form dH = w2 * g * [h > 0] for both MLPs, back-propagate it to the 72 + 72 feature
+// rows with two more tensor-core GEMMs (N = 80), and scatter d(plane*line) to the plane / line gradients and to
+// d/d(xyz_prime) straight from TMEM.  Layer inputs and dH are streamed feature-major to global memory for the
+// weight-gradient GEMMs (dynrf_wgrad_gemm); layer-2 weight / bias gradients and the layer-1 bias gradient are reduced
+// in registers with a warp transpose-reduction.
+//
+// TMEM columns: [0,128) layer-1 pre-activations (density | blending) | [128,208) d feat density | [208,288) d feat blending
+#include "dynrf_tc.cuh"
+
+namespace dynrf {
+
+constexpr int kSbbChunks = 13;
+__host__ __device__ constexpr int sbb_rows(int j) { return j < 2 ? 32 : (j == 2 ? 16 : (j < 9 ? 24 : 32)); }
+__host__ __device__ constexpr int sbb_n(int j) { return j < 3 ? 128 : (j < 9 ? 64 : 80); }
+__host__ __device__ constexpr int sbb_woff(int j) {
+  int o = 0;
+  for (int i = 0; i < j; ++i) o += 2 * sbb_n(i) * sbb_rows(i);
+  return o;
+}
+constexpr int kSbbWFloats = sbb_woff(kSbbChunks);
+constexpr int kSbbCst = 128 + 128 + 2;  // b1cat | w2cat | b2cat
+// XT rows: 80 position/time | 72 density feat | 72 blending feat | ones (225)
+
+struct SbBwdArgs {
+  const float* wq;
+  const float* cst;
+  const float* xyz;
+  const float* xyz_prime;
+  const uint8_t* valid;
+  const float* tfeat;
+  const float* gsigma;  // [P] d loss / d sigma   (or NULL)
+  const float* gblend;  // [P] d loss / d blending (or NULL)
+  int P, S, ld;
+  float* XT;    // [225][ld]
+  float* DHT;   // [128][ld]
+  float* gxp;   // [P][3] +=
+  float* gw2;   // [128] += (density | blending layer-2 weight gradients)
+  float* gb1;   // [128] +=
+  float* gb2;   // [2]   +=
+};
+
+struct TapsSmemB {
+  int4 t[9][kTileM];  // (i0 | v0 << 30, i1 | v1 << 30, raw w0 bits, raw w1 bits)
+};
+
+__device__ __forceinline__ Tap1 load_tap1(const TapsSmemB& ts, int si, int axis, int m, int G) {
+  const int4 v = ts.t[si * 3 + axis][m];
+  Tap1 t;
+  t.v0 = (v.x >> 30) & 1;
+  t.v1 = (v.y >> 30) & 1;
+  t.i0 = v.x & 0x3fffffff;
+  t.i1 = v.y & 0x3fffffff;
+  t.r0 = __int_as_float(v.z);
+  t.r1 = __int_as_float(v.w);
+  t.w0 = t.v0 ? t.r0 : 0.f;
+  t.w1 = t.v1 ? t.r1 : 0.f;
+  const int s = 1 << si;
+  t.scale = 0.5f * (float)((G + s - 1) / s - 1);
+  return t;
+}
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float4& r) {
+  uint32_t a, b, c, d;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+  r = make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
+}
+
+// v[c] holds this lane's value of column c; returns (in lane L) the sum over the 32 lanes of column L
+__device__ __forceinline__ float warp_col_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+constexpr size_t kSbbSmem = (size_t)(3 * kOpFloats + 2 * kWSlotFloats + kSbbCst + 4 * kTileM + 2 * kTileM) * sizeof(float) +
+                            sizeof(TapsSmemB) + sizeof(TileScratch<kTileM>) + 128;
+
+__global__ void __launch_bounds__(kTc3Threads, 1)
+k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_vm_grad_t gden, dynrf_vm_grad_t gbl, SbBwdArgs a) {
+  extern __shared__ __align__(128) float smem[];
+  float* abuf = smem;
+  float* wbuf = abuf + 3 * kOpFloats;
+  float* cst = wbuf + 2 * kWSlotFloats;
+  float* part = cst + kSbbCst;     // [4][128]
+  float* go = part + 4 * kTileM;   // [2][128]
+  TapsSmemB& taps = *reinterpret_cast<TapsSmemB*>(go + 2 * kTileM + 2);
+  TileScratch<kTileM>& scr = *reinterpret_cast<TileScratch<kTileM>*>(reinterpret_cast<uint8_t*>(&taps) + sizeof(TapsSmemB));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(&scr) + sizeof(TileScratch<kTileM>));
+  uint64_t* bar_free = bars;
+  uint64_t* bar_w = bars + 3;
+  uint64_t* bar_full = bars + 5;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) umma::mbar_init(&bars[i], 1);
+    for (int i = 0; i < 3; ++i) umma::mbar_init(&bar_full[i], kProdThreads / 32);
+    umma::fence_mbar_init();
+  }
+  for (int i = tid; i < kSbbCst; i += kTc3Threads) cst[i] = __ldg(a.cst + i);
+  if (warp == 0) umma::tmem_alloc(tslot, 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  Ring ring{bar_free, bar_w, abuf, wbuf, 0u, *tslot};
+  const int P = a.P;
+  const int ntiles = (P + kTileM - 1) / kTileM;
+  const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const uint32_t total_chunks = (uint32_t)my_tiles * kSbbChunks;
+  const float* b1cat = cst;
+  const float* w2cat = cst + 128;
+  const float* b2cat = cst + 256;
+
+  if (warp == kProdThreads / 32) {
+    if (lane == 0 && total_chunks > 0) {
+      ring_prefetch_w(ring, 0, a.wq + sbb_woff(0), 2u * sbb_n(0) * sbb_rows(0) * 4u);
+      for (uint32_t c = 0; c < total_chunks; ++c) {
+        const int j = (int)(c % kSbbChunks);
+        ring.chunk = c;
+        umma::mbar_wait(&bar_full[c % 3], (c / 3) & 1);
+        if (j < 3) ring_issue<128>(ring, sbb_rows(j), 0u, j == 0);
+        else if (j < 9) ring_issue<64>(ring, sbb_rows(j), ((j - 3) & 1) ? 64u : 0u, false);
+        else ring_issue<80>(ring, sbb_rows(j), j < 11 ? 128u : 208u, j == 9 || j == 11);
+        if (c + 1 < total_chunks) {
+          const int nj = (j + 1) % kSbbChunks;
+          ring_prefetch_w(ring, c + 1, a.wq + sbb_woff(nj), 2u * sbb_n(nj) * sbb_rows(nj) * 4u);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int m = tid & (kTileM - 1), prt = tid >> 7;
+    const int q = warp & 3, cb = warp >> 2;
+    const int em = q * 32 + lane;
+    const AabbNorm nb = make_norm(cfg);
+    const int G[3] = {vden.W[0], vden.H[0], vden.L[0]};
+    const int ld = a.ld;
+    float accW2 = 0.f, accB1 = 0.f, accB2 = 0.f;
+
+    auto wait_chunk = [&](uint32_t c) {
+      umma::mbar_wait(&bar_free[c % 3], (c / 3) & 1);
+      umma::fence_after_sync();
+    };
+    auto arrive = [&]() {
+      umma::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[ring.chunk % 3]);
+      ring.chunk++;
+    };
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int i0g = tile * kTileM;
+      if (tid < kTileM) {
+        const int i = i0g + tid;
+        const bool in = i < P;
+        scr.ray[tid] = in ? i / a.S : -1;
+        scr.on[tid] = (in && a.valid[i] != 0) ? 1 : 0;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+          const float x = in ? __ldg(a.xyz + (size_t)i * 3 + ax) : 0.f;
+          const float xp = in ? __ldg(a.xyz_prime + (size_t)i * 3 + ax) : 0.f;
+          scr.xn[ax][tid] = in ? norm_coord(x, nb.mn[ax], nb.inv[ax]) : 0.f;
+          scr.xq[ax][tid] = norm_coord(xp, nb.mn[ax], nb.inv[ax]);
+          scr.gx[ax][tid] = 0.f;
+        }
+      }
+      prod_bar();
+      for (int item = tid; item < 9 * kTileM; item += kProdThreads) {
+        const int mm = item & (kTileM - 1), t = item >> 7;
+        const int si = t / 3, ax = t % 3;
+        const Tap1 tp = make_tap(scr.xq[ax][mm], ax == 0 ? G[0] : (ax == 1 ? G[1] : G[2]), 1 << si);
+        taps.t[t][mm] = make_int4(tp.i0 | ((int)tp.v0 << 30), tp.i1 | ((int)tp.v1 << 30), __float_as_int(tp.r0), __float_as_int(tp.r1));
+      }
+      prod_bar();
+      const bool act = scr.on[m] != 0;
+      const uint32_t base = ring.chunk;
+      // ---- layer-1 operand chunks (same K order as the forward kernel), streamed to XT
+#pragma unroll 1
+      for (int j = 0; j < 9; ++j) {
+        ring_wait_free(ring);
+        float* buf = ring_abuf(ring);
+        if (j < 3) {
+          const int u0 = j * 5, nu = (j == 2) ? 4 : 5;
+          for (int u = prt; u < nu; u += 4) produce_pos_unit(u0 + u, scr, a.tfeat, m, buf, a.XT + (size_t)(j * 32) * ld, ld, i0g + m);
+          if (j == 0 && prt == 1) a.XT[(size_t)224 * ld + i0g + m] = act ? 1.f : 0.f;
+        } else {
+          const int si = (j - 3) >> 1;
+          const bool isbl = ((j - 3) & 1) != 0;
+          const int xrow = (isbl ? 152 : 80) + si * 24;
+          {
+            const float* pp = isbl ? vbl.plane[0] : vden.plane[0];
+            const float* ll = isbl ? vbl.line[0] : vden.line[0];
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (act) r = vm_group(pp, ll, 16, G[0], load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 1, m, G[1]), load_tap1(taps, si, 2, m, G[2]), prt * 4);
+            store_quad(buf, m, prt, r);
+            store_quad_g(a.XT, ld, xrow + prt * 4, i0g + m, r);
+          }
+          if (prt < 2) {
+            const float* pp = prt == 0 ? (isbl ? vbl.plane[1] : vden.plane[1]) : (isbl ? vbl.plane[2] : vden.plane[2]);
+            const float* ll = prt == 0 ? (isbl ? vbl.line[1] : vden.line[1]) : (isbl ? vbl.line[2] : vden.line[2]);
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int au = prt == 0 ? 0 : 1, al = prt == 0 ? 1 : 0;
+            if (act) r = vm_group(pp, ll, 4, G[au], load_tap1(taps, si, au, m, G[au]), load_tap1(taps, si, 2, m, G[2]), load_tap1(taps, si, al, m, G[al]), 0);
+            store_quad(buf, m, 4 + prt, r);
+            store_quad_g(a.XT, ld, xrow + 16 + prt * 4, i0g + m, r);
+          }
+        }
+        arrive();
+      }
+      // ---- epilogue A: layer 2, activation derivatives, dH -> data-gradient operand chunks, DHT, register reductions
+      wait_chunk(base + 8);
+      {
+        float h[32];
+        umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 32, h);
+        const bool on = scr.on[em] != 0;
+        float po = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const int n = cb * 32 + jj;
+          h[jj] = on ? fmaxf(h[jj] + b1cat[n], 0.f) : 0.f;
+          po = fmaf(h[jj], w2cat[n], po);
+        }
+        part[cb * kTileM + em] = po;
+        prod_bar();
+        if (tid < 2 * kTileM) {
+          const int which = tid >> 7, mm = tid & (kTileM - 1);
+          const int i = i0g + mm;
+          float g = 0.f;
+          if (scr.on[mm]) {
+            const float o = part[(2 * which) * kTileM + mm] + part[(2 * which + 1) * kTileM + mm] + b2cat[which];
+            if (which == 0) {
+              g = a.gsigma ? __ldg(a.gsigma + i) : 0.f;
+              if (cfg.act == DYNRF_ACT_RELU) g = o > 0.f ? g : 0.f;
+              else g *= sigmoidf_(o + cfg.density_shift);
+            } else {
+              const float sg = sigmoidf_(o);
+              g = (a.gblend ? __ldg(a.gblend + i) : 0.f) * sg * (1.0f - sg);
+            }
+          }
+          go[which * kTileM + mm] = g;
+          accB2 += g;
+        }
+        prod_bar();
+        const float gm = go[(cb >> 1) * kTileM + em];
+        float red[32];
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) red[jj] = h[jj] * gm;  // d w2[n] contributions
+        accW2 += warp_col_reduce32(red, lane);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          h[jj] = h[jj] > 0.f ? w2cat[cb * 32 + jj] * gm : 0.f;  // dH
+          red[jj] = h[jj];
+        }
+        accB1 += warp_col_reduce32(red, lane);
+#pragma unroll 1
+        for (int c4 = 0; c4 < 4; ++c4) {
+          ring_wait_free(ring);
+          if (c4 == cb) {
+            float* buf = ring_abuf(ring);
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+              const float4 v = make_float4(h[qq * 4], h[qq * 4 + 1], h[qq * 4 + 2], h[qq * 4 + 3]);
+              store_quad(buf, em, qq, v);
+              store_quad_g(a.DHT, ld, cb * 32 + qq * 4, i0g + em, v);
+            }
+          }
+          arrive();
+        }
+      }
+      // ---- epilogue B: d feat (TMEM) -> plane / line gradients + coordinate gradients
+      wait_chunk(base + 12);
+#pragma unroll 1
+      for (int tb = 0; tb < 2; ++tb) {
+        const uint32_t colbase = 128u + 80u * tb;
+#pragma unroll 1
+        for (int si = 0; si < 3; ++si) {
+          float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+          {
+            float4 g4;
+            tmem_ld4(ring.tmem + ((uint32_t)(q * 32) << 16) + colbase + si * 24 + prt * 4, g4);
+            if (act) {
+              const float* pp = tb ? vbl.plane[0] : vden.plane[0];
+              const float* ll = tb ? vbl.line[0] : vden.line[0];
+              float* gp = tb ? gbl.plane[0] : gden.plane[0];
+              float* gl = tb ? gbl.line[0] : gden.line[0];
+              const float3 r = vm_group_bwd(pp, ll, gp, gl, 16, G[0], load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 1, m, G[1]),
+                                            load_tap1(taps, si, 2, m, G[2]), prt * 4, g4);
+              g0 += r.x;
+              g1 += r.y;
+              g2 += r.z;
+            }
+          }
+          if (prt < 2) {  // warp-uniform
+            float4 g4;
+            tmem_ld4(ring.tmem + ((uint32_t)(q * 32) << 16) + colbase + si * 24 + 16 + prt * 4, g4);
+            if (act) {
+              const float* pp = prt == 0 ? (tb ? vbl.plane[1] : vden.plane[1]) : (tb ? vbl.plane[2] : vden.plane[2]);
+              const float* ll = prt == 0 ? (tb ? vbl.line[1] : vden.line[1]) : (tb ? vbl.line[2] : vden.line[2]);
+              float* gp = prt == 0 ? (tb ? gbl.plane[1] : gden.plane[1]) : (tb ? gbl.plane[2] : gden.plane[2]);
+              float* gl = prt == 0 ? (tb ? gbl.line[1] : gden.line[1]) : (tb ? gbl.line[2] : gden.line[2]);
+              if (prt == 0) {  // plane (x, z), line y
+                const float3 r = vm_group_bwd(pp, ll, gp, gl, 4, G[0], load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 2, m, G[2]),
+                                              load_tap1(taps, si, 1, m, G[1]), 0, g4);
+                g0 += r.x;
+                g2 += r.y;
+                g1 += r.z;
+              } else {  // plane (y, z), line x
+                const float3 r = vm_group_bwd(pp, ll, gp, gl, 4, G[1], load_tap1(taps, si, 1, m, G[1]), load_tap1(taps, si, 2, m, G[2]),
+                                              load_tap1(taps, si, 0, m, G[0]), 0, g4);
+                g1 += r.x;
+                g2 += r.y;
+                g0 += r.z;
+              }
+            }
+          }
+          if (act) {
+            atomicAdd(&scr.gx[0][m], g0);
+            atomicAdd(&scr.gx[1][m], g1);
+            atomicAdd(&scr.gx[2][m], g2);
+          }
+        }
+      }
+      umma::fence_before_sync();
+      prod_bar();
+      if (tid < kTileM && scr.on[tid]) {
+        const int i = i0g + tid;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) a.gxp[(size_t)i * 3 + ax] += scr.gx[ax][tid] * nb.inv[ax];
+      }
+      prod_bar();
+    }
+    atomicAdd(a.gw2 + cb * 32 + lane, accW2);
+    atomicAdd(a.gb1 + cb * 32 + lane, accB1);
+    if (tid < 2 * kTileM) {
+      const float s2 = warp_sum(accB2);
+      if (lane == 0) atomicAdd(a.gb2 + (tid >> 7), s2);
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(ring.tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// packing: chunks 0..8 exactly as the forward kernel (k_pack_sb_umma), chunks 9..12 the data-gradient operands
+//   B[k < 80][nn < 32] = W1x[32 c + nn][feat k]  (k < 72), x = density for chunks 9,10, blending for 11,12
+
+__global__ void k_pack_sb_bwd(const float* __restrict__ w_den /*[64][152]*/, const float* __restrict__ w_bl, float* __restrict__ wq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kSbbWFloats / 2) return;
+  int j = 0, base = 0;
+  for (; j < kSbbChunks; ++j) {
+    const int sz = sbb_n(j) * sbb_rows(j);
+    if (i < base + sz) break;
+    base += sz;
+  }
+  const int N = sbb_n(j), rows = sbb_rows(j);
+  const int e = i - base;
+  const int r = e / rows, k = e % rows;
+  float v = 0.f;
+  if (j < 3) {
+    const int col = 72 + pos_src_index(j * 32 + k);
+    v = r < 64 ? __ldg(w_den + (size_t)r * 152 + col) : __ldg(w_bl + (size_t)(r - 64) * 152 + col);
+  } else if (j < 9) {
+    const int col = ((j - 3) >> 1) * 24 + k;
+    v = ((j - 3) & 1) ? __ldg(w_bl + (size_t)r * 152 + col) : __ldg(w_den + (size_t)r * 152 + col);
+  } else {
+    const float* w = j < 11 ? w_den : w_bl;
+    const int nn = 32 * ((j - 9) & 1) + k;
+    v = r < 72 ? __ldg(w + (size_t)nn * 152 + r) : 0.f;
+  }
+  float hi, lo;
+  umma::split_tf32(v, hi, lo);
+  const uint32_t off = umma::kmajor_off(r, k, N) >> 2;
+  float* blob = wq + sbb_woff(j);
+  blob[off] = hi;
+  blob[N * rows + off] = lo;
+}
+
+__global__ void k_sb_bwd_colmap(int32_t* __restrict__ map /*[80]*/) {
+  const int r = threadIdx.x;
+  if (r < 80) map[r] = 72 + pos_src_index(r);
+}
+
+}  // namespace dynrf
+
+using namespace dynrf;
+
+extern "C" {
+
+int dynrf_sb_bwd_wfloats(void) { return kSbbWFloats; }
+
+int dynrf_pack_sb_bwd(const float* w_den, const float* w_bl, float* wq, int32_t* colmap80, void* stream) {
+  if (!w_den || !w_bl || !wq || !colmap80) return DYNRF_E_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  k_pack_sb_bwd<<<(kSbbWFloats / 2 + 255) / 256, 256, 0, st>>>(w_den, w_bl, wq);
+  k_sb_bwd_colmap<<<1, 96, 0, st>>>(colmap80);
+  DYNRF_CHECK_LAUNCH();
+  return 0;
+}
+
+int dynrf_dyn_mlp_bwd_tc(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density, const dynrf_vm_t* blending,
+                         const dynrf_vm_grad_t* gdensity, const dynrf_vm_grad_t* gblending, const float* wq, const float* cst,
+                         const float* xyz, const float* xyz_prime, const uint8_t* valid, const float* tfeat, const float* gsigma,
+                         const float* gblend, int N, int S, int ld, float* XT, float* DHT, float* gxp, float* gw2, float* gb1,
+                         float* gb2, void* stream) {
+  if (!cfg || !density || !blending || !gdensity || !gblending || !wq || !cst || !xyz || !xyz_prime || !valid || !tfeat || !XT || !DHT ||
+      !gxp || !gw2 || !gb1 || !gb2 || N <= 0 || S <= 0 || (ld & 3) || ld < ((N * S + kTileM - 1) / kTileM) * kTileM)
+    return DYNRF_E_ARG;
+  for (int i = 0; i < 3; ++i) {
+    const int c = i == 0 ? 16 : 4;
+    if (density->C[i] != c || blending->C[i] != c) return DYNRF_E_UNSUPPORTED;
+    if (density->H[i] != blending->H[i] || density->W[i] != blending->W[i] || density->L[i] != blending->L[i]) return DYNRF_E_UNSUPPORTED;
+  }
+  if ((uintptr_t)wq & 15) return DYNRF_E_ALIGN;
+  cudaError_t e = cudaFuncSetAttribute(k_dyn_mlp_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSbbSmem);
+  if (e != cudaSuccess) return (int)e;
+  SbBwdArgs a{wq, cst, xyz, xyz_prime, valid, tfeat, gsigma, gblend, N * S, S, ld, XT, DHT, gxp, gw2, gb1, gb2};
+  const int grid = min((N * S + kTileM - 1) / kTileM, sm_count());
+  k_dyn_mlp_bwd_tc<<<grid, kTc3Threads, kSbbSmem, reinterpret_cast<cudaStream_t>(stream)>>>(*cfg, *density, *blending, *gdensity, *gblending, a);
+  DYNRF_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -48,7 +48,7 @@ def pack_bwd(pl: ops.PackedLayer, k0: int, k1: int, nrows: int) -> torch.Tensor:
     """wb[n][j] = W[n][k0+j]; cached on the PackedLayer per parameter version."""
     cache = pl.__dict__.setdefault("_bwd_cache", {})
     key = (k0, k1, nrows)
-    ver = (pl.weight.data_ptr(), pl.weight._version)
+    ver = (ops.PARAM_EPOCH[0], pl.weight.data_ptr(), pl.weight._version)
     hit = cache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]
@@ -232,8 +232,11 @@ class DynamicFieldFn(torch.autograd.Function):
                     "dynrf_dyn_app_bwd")
         vden = ops.vm_struct(m.density_plane, m.density_line)
         vbl = ops.vm_struct(m.blending_plane, m.blending_line)
+        tc_sb = None
+        if ops.USE_TC:
+            tc_sb = _dyn_mlp_bwd_tc(m, cfg, r, vden, vbl, gden, gbl, gsig, _f32c(gblend) if gblend is not None else None, gxp, n, s)
         for mode, vm, gvm, k1, k2, gout in ((0, vden, gden, "d1", "d2", gsig), (1, vbl, gbl, "b1", "b2", gblend)):
-            if gout is None:
+            if gout is None or tc_sb is not None:
                 continue
             wbf = pack_bwd(pk[k1], 0, 72, 64)
             L.check(lib.dynrf_dyn_mlp_bwd(C.byref(cfg), mode, C.byref(vm), C.byref(gvm), C.byref(ly[k1]), C.byref(ly[k2]), _p(wbf),
@@ -254,6 +257,8 @@ class DynamicFieldFn(torch.autograd.Function):
         for k in _DYN_LAYER_ORDER:
             if tc_head is not None and k in tc_head:
                 dw, db = tc_head[k]
+            elif tc_sb is not None and k in tc_sb:
+                dw, db = tc_sb[k]
             else:
                 dw, db = gl[k].unpack()
             pg.append(dw)
@@ -272,12 +277,13 @@ class _HeadBwdState:
         self.cst = torch.empty(lib.dynrf_head_bwd_cst_floats(), device=dev)
         self.colmap = torch.empty(113, dtype=torch.int32, device=dev)
         self.key = None
+        self.src_rows = None
         self.bufs = {}
 
     def refresh(self, m):
         rm = m.renderModule
         l1, l2, l3 = rm.mlp[0], rm.mlp[2], rm.mlp_view[0]
-        key = tuple((p.data_ptr(), p._version) for p in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias))
+        key = (ops.PARAM_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias))
         if key != self.key:
             with torch.no_grad():
                 L.check(L.load().dynrf_pack_head_bwd(_p(_f32c(l1.weight.detach())), _p(_f32c(l2.weight.detach())), _p(self.wq),
@@ -285,9 +291,10 @@ class _HeadBwdState:
                 w3 = l3.weight.detach()
                 torch.cat((l1.bias.detach(), l2.bias.detach(), w3[:, :128].t().reshape(-1), w3[:, 128:131].t().reshape(-1),
                            l3.bias.detach()), out=self.cst)
-                cm = self.colmap.long()
-                self.src_rows = torch.nonzero(cm >= 0).reshape(-1)     # X1T rows that map to a layer-1 input column
-                self.dst_cols = cm[self.src_rows]
+                if self.src_rows is None:                                   # constant map, resolved once (host sync)
+                    cm = self.colmap.long()
+                    self.src_rows = torch.nonzero(cm >= 0).reshape(-1)     # X1T rows that map to a layer-1 input column
+                    self.dst_cols = cm[self.src_rows]
             self.key = key
         return self
 
@@ -343,6 +350,69 @@ def _dyn_head_bwd_tc(m, cfg, r, grgb, gl, gapp, gxp, n, s):
     return {"h1": (dw1, db1), "h2": (dw2, db2.reshape(-1)), "h3": (dw3, gb3)}
 
 
+class _SbBwdState:
+    """Per-model packed weights / constants / scratch of the tensor-core density + blending backward."""
+
+    def __init__(self, m):
+        lib = L.load()
+        dev = m.density_layer1.weight.device
+        self.wq = torch.empty(lib.dynrf_sb_bwd_wfloats(), device=dev)
+        self.cst = torch.empty(258, device=dev)
+        self.colmap = torch.empty(80, dtype=torch.int32, device=dev)
+        self.key = None
+        self.cols = None
+        self.bufs = {}
+
+    def refresh(self, m):
+        ps = [m.density_layer1.weight, m.density_layer1.bias, m.density_layer2.weight, m.density_layer2.bias,
+              m.blending_layer1.weight, m.blending_layer1.bias, m.blending_layer2.weight, m.blending_layer2.bias]
+        key = (ops.PARAM_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self.key:
+            with torch.no_grad():
+                L.check(L.load().dynrf_pack_sb_bwd(_p(_f32c(ps[0].detach())), _p(_f32c(ps[4].detach())), _p(self.wq), _p(self.colmap),
+                                                   _stream()), "dynrf_pack_sb_bwd")
+                torch.cat((ps[1].detach(), ps[5].detach(), ps[2].detach().reshape(-1), ps[6].detach().reshape(-1),
+                           ps[3].detach().reshape(-1), ps[7].detach().reshape(-1)), out=self.cst)
+                if self.cols is None:
+                    self.cols = self.colmap.long()
+            self.key = key
+        return self
+
+    def scratch(self, ld, dev):
+        b = self.bufs.get(ld)
+        if b is None:
+            b = self.bufs[ld] = dict(XT=torch.empty(225, ld, device=dev), DHT=torch.empty(128, ld, device=dev))
+        return b
+
+
+def _dyn_mlp_bwd_tc(m, cfg, r, vden, vbl, gden, gbl, gsig, gblend, gxp, n, s):
+    """Tensor-core backward of the density + blending MLPs (a16 + a17): one fused tile kernel + one wgrad GEMM."""
+    lib = L.load()
+    st = m.__dict__.get("_sb_bwd_state")
+    if st is None:
+        st = m.__dict__["_sb_bwd_state"] = _SbBwdState(m)
+    st.refresh(m)
+    dev = gxp.device
+    P = n * s
+    ld = ops.round_up(P, 128)
+    b = st.scratch(ld, dev)
+    gsmall = torch.zeros(258, device=dev)      # gw2 (128) | gb1 (128) | gb2 (2)
+    L.check(lib.dynrf_dyn_mlp_bwd_tc(C.byref(cfg), C.byref(vden), C.byref(vbl), C.byref(gden), C.byref(gbl), _p(st.wq), _p(st.cst),
+                                     _p(r["xyz"]), _p(r["xyz_prime"]), _p(r["valid"]), _p(r["tfeat"]), _p(gsig), _p(gblend), n, s, ld,
+                                     _p(b["XT"]), _p(b["DHT"]), _p(gxp), _p(gsmall), _p(gsmall[128:]), _p(gsmall[256:]), _stream()),
+            "dynrf_dyn_mlp_bwd_tc")
+    dwf = torch.zeros(128, 224, device=dev)
+    L.check(lib.dynrf_wgrad_gemm(_p(b["XT"]), ld, 224, _p(b["DHT"]), ld, 128, P, None, _p(dwf), 224, _stream()), "dynrf_wgrad_gemm")
+    dw_d = torch.empty(64, 152, device=dev)
+    dw_b = torch.empty(64, 152, device=dev)
+    dw_d[:, :72] = dwf[:64, 80:152]
+    dw_b[:, :72] = dwf[64:, 152:224]
+    dw_d[:, st.cols] = dwf[:64, :80]
+    dw_b[:, st.cols] = dwf[64:, :80]
+    return {"d1": (dw_d, gsmall[128:192]), "d2": (gsmall[:64].reshape(1, 64), gsmall[256:257]),
+            "b1": (dw_b, gsmall[192:256]), "b2": (gsmall[64:128].reshape(1, 64), gsmall[257:258])}
+
+
 def field_forward_with_grad(model, rays, ts, xyz, z_vals, valid, ray_type):
     if model.is_dynamic:
         blend, weight, xyzp, rgb, sigma, dists = DynamicFieldFn.apply(model, ray_type, rays, ts, xyz, z_vals, valid,
@@ -390,26 +460,63 @@ class CompositeFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------- the timed train step
 
 
-def train_step(step, rays, ts, target):
-    """fwd + bwd of both fields through the public API, MSE on the three composited colours, Adam update."""
+def _train_setup(step):
+    static, dyn = step.static, step.dyn
+    params = list(static.parameters()) + [p for n_, p in dyn.named_parameters() if not n_.startswith("scene_flow")]
+    step.params = params
+    # one flat gradient buffer; every p.grad is a view into it, so a data-parallel step all-reduces one tensor and the
+    # buffer addresses are stable under CUDA-graph replay.  Views keep each parameter's own (channel-last) strides.
+    total = sum(p.numel() for p in params)
+    step.flat_grad = torch.zeros(total, device=params[0].device)
+    off = 0
+    for p in params:
+        k = p.numel()
+        p.grad = torch.as_strided(step.flat_grad, p.shape, p.stride(), off) if _dense(p) else step.flat_grad[off:off + k].view(p.shape)
+        off += k
+    step.opt = torch.optim.Adam(params, lr=1e-4, betas=(0.9, 0.99), capturable=True, foreach=True)
+
+
+def _dense(p):
+    """True if p's strides are a permutation of a dense layout over numel() elements (safe to alias with as_strided)."""
+    if p.is_contiguous():
+        return True
+    sz_st = sorted(((st, sz) for sz, st in zip(p.shape, p.stride()) if sz > 1))
+    exp = 1
+    for st, sz in sz_st:
+        if st != exp:
+            return False
+        exp *= sz
+    return True
+
+
+def train_fwd_bwd(step, rays, ts, target):
+    """fwd + bwd of both fields through the public API, MSE on the three composited colours; gradients land in step.flat_grad."""
     import renderer as R
 
     static, dyn = step.static, step.dyn
     if getattr(step, "opt", None) is None:
-        params = list(static.parameters()) + [p for n_, p in dyn.named_parameters() if not n_.startswith("scene_flow")]
-        step.params = params
-        step.opt = torch.optim.Adam(params, lr=1e-4, betas=(0.9, 0.99))
-    xyz, z, valid = R.sampleXYZ(dyn, rays, step.s, step.rt, True)
+        _train_setup(step)
+    step.flat_grad.zero_()
+    xyz, z, valid = R.sampleXYZ(dyn, rays, step.s, step.rt, getattr(step, "jitter", True))
     fs = static(rays, ts, None, xyz, z, valid, is_train=True, ray_type=step.rt, N_samples=step.s)
     fd = dyn(rays, ts, None, xyz, z, valid, is_train=True, ray_type=step.rt, N_samples=step.s)
     o = R.raw2outputs(fs[6], fs[7], fd[6], fd[7], fd[9], fd[2], fd[8], rays, False, step.rt)
     loss = ((o[0] - target) ** 2).mean() + ((o[4] - target) ** 2).mean() + ((o[8] - target) ** 2).mean()
-    step.opt.zero_grad(set_to_none=True)
     loss.backward()
-    from .parallel import allreduce_mean_grads
-
-    allreduce_mean_grads(step.params, step.world)
-    step.opt.step()
     out = torch.cat((o[0], o[1][:, None], o[2][:, None], o[4], o[5][:, None], o[6][:, None], o[8], o[9][:, None],
                      o[10][:, None], o[12][:, None]), -1).detach()
+    return out
+
+
+def train_update(step):
+    step.opt.step()
+
+
+def train_step(step, rays, ts, target):
+    """One data-parallel optimisation step: local fwd + bwd, one all-reduce of the flat gradient, Adam."""
+    from .parallel import allreduce_flat_mean
+
+    out = train_fwd_bwd(step, rays, ts, target)
+    allreduce_flat_mean(step.flat_grad, step.world)
+    train_update(step)
     return out

@@ -117,7 +117,7 @@ class PackedLayer:
         self.struct = L.LayerT(self.wt.data_ptr(), self.b.data_ptr(), self.K, self.N, self.Kpad, self.Npad)
 
     def refresh(self) -> L.LayerT:
-        key = (self.weight.data_ptr(), self.weight._version, None if self.bias is None else self.bias._version)
+        key = (PARAM_EPOCH[0], self.weight.data_ptr(), self.weight._version, None if self.bias is None else self.bias._version)
         if key != self._key:
             w = _f32c(self.weight.detach())
             b = None if self.bias is None else _f32c(self.bias.detach())
@@ -141,7 +141,7 @@ class PackedUmmaLayer:
         self.struct = L.UmmaLayerT(self.wq.data_ptr(), self.b.data_ptr(), self.K, self.N, self.Npad, self.nchunks)
 
     def refresh(self) -> L.UmmaLayerT:
-        key = (self.weight.data_ptr(), self.weight._version, None if self.bias is None else self.bias._version)
+        key = (PARAM_EPOCH[0], self.weight.data_ptr(), self.weight._version, None if self.bias is None else self.bias._version)
         if key != self._key:
             w = _f32c(self.weight.detach())
             b = None if self.bias is None else _f32c(self.bias.detach())
@@ -154,6 +154,9 @@ class PackedUmmaLayer:
 # tensor-core (tcgen05) kernels for the MLP stages that have them; the SIMT fp32 kernels stay in the library
 # as a cross-check (tests flip this flag to compare the two)
 USE_TC = True
+# Bumped whenever parameters may have changed without their autograd version counters moving (a CUDA-graph replay of a
+# train step updates the weights in place on the device): every packed-operand cache includes it in its key.
+PARAM_EPOCH = [0]
 TC_SB_VERSION = 2
 
 
@@ -186,7 +189,7 @@ class PackedSigmaBlend:
         m = self.m
         ps = [m.density_layer1.weight, m.density_layer1.bias, m.density_layer2.weight, m.density_layer2.bias,
               m.blending_layer1.weight, m.blending_layer1.bias, m.blending_layer2.weight, m.blending_layer2.bias]
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        key = (PARAM_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in ps)
         if key != self._key:
             with torch.no_grad():
                 wd, wb = _f32c(ps[0].detach()), _f32c(ps[4].detach())

@@ -54,3 +54,13 @@ def allreduce_mean_grads(params: Iterable[torch.nn.Parameter], world: int) -> No
         k = g.numel()
         g.copy_(flat[off:off + k].view_as(g))
         off += k
+
+
+def allreduce_flat_mean(flat: torch.Tensor, world: int) -> None:
+    """Mean over ranks of a flat gradient buffer that every p.grad aliases (one collective, in place)."""
+    if world == 1:
+        return
+    import torch.distributed as dist
+
+    dist.all_reduce(flat)
+    flat.div_(world)

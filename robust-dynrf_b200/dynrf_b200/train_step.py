@@ -25,11 +25,20 @@ def backward_available() -> bool:
 
 
 class Step:
-    def __init__(self, static, dyn, n_samples, ray_type, mode, world=1):
+    """graph=True captures the whole step (public-API calls, autograd backward, Adam) into CUDA graphs after three eager
+    warm-up steps and replays them: the step is ~120 kernel launches and ~300 small tensor ops, and at ~20 ms of GPU
+    work per step the Python / launch overhead is of the same size.  With world > 1 the collectives stay eager between
+    two graphs (forward+backward | optimizer)."""
+
+    def __init__(self, static, dyn, n_samples, ray_type, mode, world=1, graph=False, jitter=True):
         if mode == "train" and not backward_available():
             raise RuntimeError("train mode needs the backward kernels (dynrf_b200.backward)")
         self.static, self.dyn, self.s, self.rt, self.mode, self.world = static, dyn, n_samples, ray_type, mode, world
         self.gather_buf = None
+        self.use_graph = graph
+        self.jitter = jitter    # stratified-sampling jitter (is_train of renderer.sampleXYZ)
+        self._g = None          # (inputs, graphs, outputs) once captured
+        self.launches_per_step = None
 
     def _gather(self, out):
         from .parallel import gather_ray_maps
@@ -39,7 +48,7 @@ class Step:
     @torch.no_grad()
     def forward_fused(self, rays, ts):
         cfg = self.dyn.native_cfg(self.rt)
-        zvec = ops.make_zvec(cfg, self.s, self.rt, True, rays.device)
+        zvec = ops.make_zvec(cfg, self.s, self.rt, self.jitter, rays.device)
         xyz, z, valid = ops.sample_points(cfg, rays, zvec)
         st = ops.static_forward_raw(self.static, rays, None, None, None, self.rt, zvec=zvec)
         st["xyz"] = xyz
@@ -53,17 +62,92 @@ class Step:
     def forward_api(self, rays, ts):
         import renderer as R
 
-        xyz, z, valid = R.sampleXYZ(self.dyn, rays, self.s, self.rt, True)
+        xyz, z, valid = R.sampleXYZ(self.dyn, rays, self.s, self.rt, self.jitter)
         fs = self.static(rays, ts, None, xyz, z, valid, is_train=True, ray_type=self.rt, N_samples=self.s)
         fd = self.dyn(rays, ts, None, xyz, z, valid, is_train=True, ray_type=self.rt, N_samples=self.s)
         o = R.raw2outputs(fs[6], fs[7], fd[6], fd[7], fd[9], fd[2], fd[8], rays, False, self.rt)
         return torch.cat((o[0], o[1][:, None], o[2][:, None], o[4], o[5][:, None], o[6][:, None], o[8], o[9][:, None],
                           o[10][:, None], o[12][:, None]), -1)
 
-    def __call__(self, rays, ts, target, fused=True):
+    # ------------------------------------------------------------------ eager pieces
+    def _compute(self, rays, ts, target, fused):
+        """Local (this rank's) part up to -- excluding -- the collectives and the optimizer update."""
         if self.mode == "fwd":
-            out = self.forward_fused(rays, ts) if fused else self.forward_api(rays, ts)
-            return self._gather(out)
+            return self.forward_fused(rays, ts) if fused else self.forward_api(rays, ts)
         from . import backward as B
 
-        return self._gather(B.train_step(self, rays, ts, target))
+        return B.train_fwd_bwd(self, rays, ts, target)
+
+    def _finish(self):
+        if self.mode == "train":
+            from . import backward as B
+
+            B.train_update(self)
+
+    def _sync_grads(self):
+        if self.mode == "train" and self.world > 1:
+            from .parallel import allreduce_flat_mean
+
+            allreduce_flat_mean(self.flat_grad, self.world)
+
+    def _eager(self, rays, ts, target, fused):
+        from . import lib as L
+
+        n0 = L.launch_count
+        out = self._compute(rays, ts, target, fused)
+        self._sync_grads()
+        self._finish()
+        self.launches_per_step = L.launch_count - n0
+        return out
+
+    # ------------------------------------------------------------------ CUDA-graph path
+    def _capture(self, rays, ts, target, fused):
+        import gc
+
+        gc.collect()   # drop autograd graphs (and their AccumulateGrad nodes, which remember a stream) of earlier eager steps
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        ins = (rays.clone(), ts.clone(), None if target is None else target.clone())
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._eager(*ins, fused)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        gc.collect()
+        g1 = torch.cuda.CUDAGraph()
+        g2 = None
+        if self.world == 1 or self.mode == "fwd":
+            with torch.cuda.graph(g1, stream=side):
+                out = self._compute(*ins, fused)
+                self._finish()
+        else:
+            with torch.cuda.graph(g1, stream=side):
+                out = self._compute(*ins, fused)
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, pool=g1.pool(), stream=side):
+                self._finish()
+        self._g = (ins, g1, g2, out, fused)
+
+    def _replay(self, rays, ts, target):
+        ins, g1, g2, out, _ = self._g
+        ins[0].copy_(rays, non_blocking=True)
+        ins[1].copy_(ts, non_blocking=True)
+        if target is not None and ins[2] is not None:
+            ins[2].copy_(target, non_blocking=True)
+        g1.replay()
+        if g2 is not None:
+            self._sync_grads()
+            g2.replay()
+        if self.mode == "train":
+            ops.PARAM_EPOCH[0] += 1   # weights moved on the device without their version counters changing
+        return out
+
+    def __call__(self, rays, ts, target, fused=True):
+        if self.mode == "train":
+            fused = False   # the train step always goes through the public API
+        if self.use_graph:
+            if self._g is None or self._g[4] != fused:
+                self._capture(rays, ts, target, fused)
+            return self._gather(self._replay(rays, ts, target))
+        return self._gather(self._eager(rays, ts, target, fused))

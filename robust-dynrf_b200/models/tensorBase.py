@@ -171,8 +171,8 @@ class TensorBase(nn.Module):
         """name -> dynrf_layer_t, repacked only when a parameter changed.  One cheap key over all layers
         (data_ptr + in-place version counter) guards the whole table so the steady state costs ~20 us."""
         tbl = self._layer_table()
-        key = tuple((lin.weight.data_ptr(), lin.weight._version, -1 if lin.bias is None else lin.bias._version)
-                    for lin in tbl.values())
+        key = (_ops.PARAM_EPOCH[0],) + tuple((lin.weight.data_ptr(), lin.weight._version, -1 if lin.bias is None else lin.bias._version)
+                                             for lin in tbl.values())
         if getattr(self, "_packed_key", None) == key:
             return self._packed_out
         out = {}
