@@ -323,16 +323,15 @@ k_static_density_bwd(dynrf_field_cfg_t cfg, dynrf_vm_t vm, dynrf_vm_grad_t gvm, 
                      const uint8_t* __restrict__ valid, const float* __restrict__ sigma, const float* __restrict__ gsig, int P,
                      float* __restrict__ gxyz) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  if (!valid[i]) return;
-  float g = __ldg(gsig + i);
+  bool act = i < P && valid[i] != 0;   // no early exits: the scatter below is warp-cooperative
+  float g = act ? __ldg(gsig + i) : 0.f;
   const AabbNorm nb = make_norm(cfg);
   float xn[3];
 #pragma unroll
-  for (int a = 0; a < 3; ++a) xn[a] = norm_coord(__ldg(xyz + (size_t)i * 3 + a), nb.mn[a], nb.inv[a]);
+  for (int a = 0; a < 3; ++a) xn[a] = act ? norm_coord(__ldg(xyz + (size_t)i * 3 + a), nb.mn[a], nb.inv[a]) : 0.f;
   if (cfg.act == DYNRF_ACT_RELU) {
-    if (!(__ldg(sigma + i) > 0.f)) return;
-  } else {
+    if (act && !(__ldg(sigma + i) > 0.f)) act = false;
+  } else if (act) {
     // softplus'(x) = sigmoid(x): recompute the feature
     float feat = 0.f;
     for (int pl = 0; pl < 3; ++pl) {
@@ -346,7 +345,8 @@ k_static_density_bwd(dynrf_field_cfg_t cfg, dynrf_vm_t vm, dynrf_vm_grad_t gvm, 
     }
     g *= sigmoidf_(feat + cfg.density_shift);
   }
-  if (g == 0.f) return;
+  if (g == 0.f) act = false;
+  if (!__any_sync(0xffffffffu, act)) return;   // warp-uniform
   float gacc[3] = {0.f, 0.f, 0.f};
   const float4 g4 = make_float4(g, g, g, g);
 #pragma unroll
@@ -355,13 +355,14 @@ k_static_density_bwd(dynrf_field_cfg_t cfg, dynrf_vm_t vm, dynrf_vm_grad_t gvm, 
     plane_axes(pl, u, v, l);
     const Tap1 tu = make_tap(xn[u], vm.W[pl], 1), tv = make_tap(xn[v], vm.H[pl], 1), tl = make_tap(xn[l], vm.L[pl], 1);
     for (int c = 0; c < vm.C[pl]; c += 4) {
-      const float3 r = vm_group_bwd(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], vm.C[pl], vm.W[pl], tu, tv, tl, c, g4);
+      const float3 r = vm_group_bwd_agg(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], vm.C[pl], vm.W[pl], tu, tv, tl, c, g4, act,
+                                        threadIdx.x & 31);
       gacc[u] += r.x;
       gacc[v] += r.y;
       gacc[l] += r.z;
     }
   }
-  if (gxyz) {
+  if (gxyz && act) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) gxyz[(size_t)i * 3 + a] += gacc[a] * nb.inv[a];
   }

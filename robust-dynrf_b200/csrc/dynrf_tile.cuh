@@ -93,14 +93,104 @@ __device__ __forceinline__ float3 vm_group_bwd(const float* __restrict__ plane, 
   return gx;
 }
 
+// ---- warp-aggregated variant ---------------------------------------------------------------------------------------
+// Lanes of a warp hold consecutive samples of one ray, so neighbouring lanes very often hit the SAME texels (NDC rays run
+// almost parallel to z: the 16/48-channel xy plane and the x / y lines see runs of 10-30 identical taps).  Identical
+// addresses serialise in the L2 atomic unit, so each run of adjacent lanes with identical taps is summed with a segmented
+// shuffle reduction and only the run head issues the reduction.  Non-adjacent duplicates simply issue separately.
+struct WarpRuns {
+  bool head;      // first lane of a run of identical keys
+  int remaining;  // lanes in [lane, end of run)
+  int maxrem;     // warp-wide maximum (uniform): 1 = no aggregation possible
+};
+__device__ __forceinline__ WarpRuns warp_runs(int k0, int k1, int lane) {
+  const int p0 = __shfl_up_sync(0xffffffffu, k0, 1), p1 = __shfl_up_sync(0xffffffffu, k1, 1);
+  const bool newrun = lane == 0 || p0 != k0 || p1 != k1;
+  const uint32_t heads = __ballot_sync(0xffffffffu, newrun);
+  const uint32_t above = lane == 31 ? 0u : (heads >> (lane + 1));
+  WarpRuns r;
+  r.head = newrun;
+  r.remaining = above ? __ffs(above) : 32 - lane;
+  r.maxrem = __reduce_max_sync(0xffffffffu, r.remaining);
+  return r;
+}
+__device__ __forceinline__ float4 seg_reduce4(float4 v, const WarpRuns& r) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    if (off >= r.maxrem) break;  // warp-uniform
+    const float ox = __shfl_down_sync(0xffffffffu, v.x, off), oy = __shfl_down_sync(0xffffffffu, v.y, off);
+    const float oz = __shfl_down_sync(0xffffffffu, v.z, off), ow = __shfl_down_sync(0xffffffffu, v.w, off);
+    if (off < r.remaining) {
+      v.x += ox;
+      v.y += oy;
+      v.z += oz;
+      v.w += ow;
+    }
+  }
+  return v;
+}
+__device__ __forceinline__ int tap_key(const Tap1& t, bool act) {
+  return act ? (t.i0 | ((int)t.v0 << 29) | ((int)t.v1 << 30)) : -1;
+}
+
+// Same contract as vm_group_bwd, but must be called by all 32 lanes of the warp (act = false for idle lanes).
+__device__ __forceinline__ float3 vm_group_bwd_agg(const float* __restrict__ plane, const float* __restrict__ line,
+                                                   float* __restrict__ gplane, float* __restrict__ gline, int C, int W,
+                                                   const Tap1& tu, const Tap1& tv, const Tap1& tl, int c, float4 g, bool act,
+                                                   int lane) {
+  const size_t o00 = ((size_t)tv.i0 * W + tu.i0) * C + c, o01 = ((size_t)tv.i0 * W + tu.i1) * C + c;
+  const size_t o10 = ((size_t)tv.i1 * W + tu.i0) * C + c, o11 = ((size_t)tv.i1 * W + tu.i1) * C + c;
+  const bool b00 = act && tu.v0 && tv.v0, b01 = act && tu.v1 && tv.v0, b10 = act && tu.v0 && tv.v1, b11 = act && tu.v1 && tv.v1;
+  const float4 P00 = b00 ? ldg4(plane + o00) : zero4(), P01 = b01 ? ldg4(plane + o01) : zero4();
+  const float4 P10 = b10 ? ldg4(plane + o10) : zero4(), P11 = b11 ? ldg4(plane + o11) : zero4();
+  const size_t l0 = (size_t)tl.i0 * C + c, l1 = (size_t)tl.i1 * C + c;
+  const bool c0 = act && tl.v0, c1 = act && tl.v1;
+  const float4 L0 = c0 ? ldg4(line + l0) : zero4(), L1 = c1 ? ldg4(line + l1) : zero4();
+  const float w00 = tu.r0 * tv.r0, w01 = tu.r1 * tv.r0, w10 = tu.r0 * tv.r1, w11 = tu.r1 * tv.r1;
+  float4 p = mul4(P00, w00);
+  p = fma4(P01, w01, p);
+  p = fma4(P10, w10, p);
+  p = fma4(P11, w11, p);
+  float4 l = mul4(L0, tl.r0);
+  l = fma4(L1, tl.r1, l);
+  const float4 dp = act ? mul44(g, l) : zero4(), dl = act ? mul44(g, p) : zero4();
+  {
+    const WarpRuns ru = warp_runs(tap_key(tu, act), tap_key(tv, act), lane);
+    const float4 d00 = seg_reduce4(b00 ? mul4(dp, w00) : zero4(), ru), d01 = seg_reduce4(b01 ? mul4(dp, w01) : zero4(), ru);
+    const float4 d10 = seg_reduce4(b10 ? mul4(dp, w10) : zero4(), ru), d11 = seg_reduce4(b11 ? mul4(dp, w11) : zero4(), ru);
+    if (ru.head) {
+      if (b00) red_add4(gplane + o00, d00.x, d00.y, d00.z, d00.w);
+      if (b01) red_add4(gplane + o01, d01.x, d01.y, d01.z, d01.w);
+      if (b10) red_add4(gplane + o10, d10.x, d10.y, d10.z, d10.w);
+      if (b11) red_add4(gplane + o11, d11.x, d11.y, d11.z, d11.w);
+    }
+  }
+  {
+    const WarpRuns ru = warp_runs(tap_key(tl, act), 0, lane);
+    const float4 e0 = seg_reduce4(c0 ? mul4(dl, tl.r0) : zero4(), ru), e1 = seg_reduce4(c1 ? mul4(dl, tl.r1) : zero4(), ru);
+    if (ru.head) {
+      if (c0) red_add4(gline + l0, e0.x, e0.y, e0.z, e0.w);
+      if (c1) red_add4(gline + l1, e1.x, e1.y, e1.z, e1.w);
+    }
+  }
+  float3 gx;
+  const float4 dpu = fma4(sub4(P11, P10), tv.r1, mul4(sub4(P01, P00), tv.r0));
+  const float4 dpv = fma4(sub4(P11, P01), tu.r1, mul4(sub4(P10, P00), tu.r0));
+  gx.x = dot4(dp, dpu) * tu.scale;
+  gx.y = dot4(dp, dpv) * tv.scale;
+  gx.z = dot4(dl, sub4(L1, L0)) * tl.scale;
+  return gx;
+}
+
 // backward of gather_vm_rows: dA rows -> plane/line gradients; coordinate gradients are added to gxs[3][TM].
 template <int TM, int LD>
 __device__ __forceinline__ void scatter_vm_rows(const dynrf_vm_t& vm, const dynrf_vm_grad_t& gvm, const float (*xq)[TM],
                                                 int stride, int row_base, const float* __restrict__ dA, int tid,
                                                 const int* __restrict__ on, float (*gxs)[TM]) {
   constexpr int NPART = kMlpThreads / TM;
+  static_assert(TM % 32 == 0, "a warp must hold 32 consecutive samples");
   const int m = tid % TM, part = tid / TM;
-  if (!on[m]) return;
+  const bool act = on[m] != 0;
   const float x3[3] = {xq[0][m], xq[1][m], xq[2][m]};
   float gacc[3] = {0.f, 0.f, 0.f};
   int q = 0, coff = 0;
@@ -115,7 +205,8 @@ __device__ __forceinline__ void scatter_vm_rows(const dynrf_vm_t& vm, const dynr
     for (int g = (part - q % NPART + NPART) % NPART; g < ng; g += NPART) {
       const float* a = dA + (size_t)(row_base + coff + g * 4) * LD + m;
       const float4 gg = make_float4(a[0], a[LD], a[2 * LD], a[3 * LD]);
-      const float3 r = vm_group_bwd(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], C, vm.W[pl], tu, tv, tl, g * 4, gg);
+      const float3 r = vm_group_bwd_agg(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], C, vm.W[pl], tu, tv, tl, g * 4, gg, act,
+                                        tid & 31);
       gacc[u] += r.x;
       gacc[v] += r.y;
       gacc[l] += r.z;
@@ -123,7 +214,7 @@ __device__ __forceinline__ void scatter_vm_rows(const dynrf_vm_t& vm, const dynr
     q += ng;
     coff += C;
   }
-  if (gxs) {
+  if (gxs && act) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) atomicAdd(&gxs[a][m], gacc[a]);
   }

@@ -290,13 +290,13 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
           {
             float4 g4;
             tmem_ld4(ring.tmem + ((uint32_t)(q * 32) << 16) + colbase + si * 24 + prt * 4, g4);
-            if (act) {
+            {
               const float* pp = tb ? vbl.plane[0] : vden.plane[0];
               const float* ll = tb ? vbl.line[0] : vden.line[0];
               float* gp = tb ? gbl.plane[0] : gden.plane[0];
               float* gl = tb ? gbl.line[0] : gden.line[0];
-              const float3 r = vm_group_bwd(pp, ll, gp, gl, 16, G[0], load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 1, m, G[1]),
-                                            load_tap1(taps, si, 2, m, G[2]), prt * 4, g4);
+              const float3 r = vm_group_bwd_agg(pp, ll, gp, gl, 16, G[0], load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 1, m, G[1]),
+                                                load_tap1(taps, si, 2, m, G[2]), prt * 4, g4, act, lane);
               g0 += r.x;
               g1 += r.y;
               g2 += r.z;
@@ -305,24 +305,22 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
           if (prt < 2) {  // warp-uniform
             float4 g4;
             tmem_ld4(ring.tmem + ((uint32_t)(q * 32) << 16) + colbase + si * 24 + 16 + prt * 4, g4);
-            if (act) {
-              const float* pp = prt == 0 ? (tb ? vbl.plane[1] : vden.plane[1]) : (tb ? vbl.plane[2] : vden.plane[2]);
-              const float* ll = prt == 0 ? (tb ? vbl.line[1] : vden.line[1]) : (tb ? vbl.line[2] : vden.line[2]);
-              float* gp = prt == 0 ? (tb ? gbl.plane[1] : gden.plane[1]) : (tb ? gbl.plane[2] : gden.plane[2]);
-              float* gl = prt == 0 ? (tb ? gbl.line[1] : gden.line[1]) : (tb ? gbl.line[2] : gden.line[2]);
-              if (prt == 0) {  // plane (x, z), line y
-                const float3 r = vm_group_bwd(pp, ll, gp, gl, 4, G[0], load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 2, m, G[2]),
-                                              load_tap1(taps, si, 1, m, G[1]), 0, g4);
-                g0 += r.x;
-                g2 += r.y;
-                g1 += r.z;
-              } else {  // plane (y, z), line x
-                const float3 r = vm_group_bwd(pp, ll, gp, gl, 4, G[1], load_tap1(taps, si, 1, m, G[1]), load_tap1(taps, si, 2, m, G[2]),
-                                              load_tap1(taps, si, 0, m, G[0]), 0, g4);
-                g1 += r.x;
-                g2 += r.y;
-                g0 += r.z;
-              }
+            const float* pp = prt == 0 ? (tb ? vbl.plane[1] : vden.plane[1]) : (tb ? vbl.plane[2] : vden.plane[2]);
+            const float* ll = prt == 0 ? (tb ? vbl.line[1] : vden.line[1]) : (tb ? vbl.line[2] : vden.line[2]);
+            float* gp = prt == 0 ? (tb ? gbl.plane[1] : gden.plane[1]) : (tb ? gbl.plane[2] : gden.plane[2]);
+            float* gl = prt == 0 ? (tb ? gbl.line[1] : gden.line[1]) : (tb ? gbl.line[2] : gden.line[2]);
+            if (prt == 0) {  // plane (x, z), line y
+              const float3 r = vm_group_bwd_agg(pp, ll, gp, gl, 4, G[0], load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 2, m, G[2]),
+                                                load_tap1(taps, si, 1, m, G[1]), 0, g4, act, lane);
+              g0 += r.x;
+              g2 += r.y;
+              g1 += r.z;
+            } else {  // plane (y, z), line x
+              const float3 r = vm_group_bwd_agg(pp, ll, gp, gl, 4, G[1], load_tap1(taps, si, 1, m, G[1]), load_tap1(taps, si, 2, m, G[2]),
+                                                load_tap1(taps, si, 0, m, G[0]), 0, g4, act, lane);
+              g1 += r.x;
+              g2 += r.y;
+              g0 += r.z;
             }
           }
           if (act) {
