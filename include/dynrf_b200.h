@@ -281,6 +281,22 @@ int dynrf_basis_bwd(const dynrf_field_cfg_t* cfg, int dynamic, const dynrf_vm_t*
                     const float* coords, const float* DFT, int ld, int N, int S, const int32_t* active_idx,
                     const int32_t* active_count, float* gbasis_wt, float* gcoord, void* stream);
 
+/* ---- tensor-core forward of the appearance stage on the active samples (static: a7+a11+a12/a13, reference
+ * models/tensorBase.py compute_appfeature + basis_mat + MLPRender_Fea / MLPRender_Fea_TimeEmbedding; dynamic: a18+a14,
+ * compute_appfeature at strides 1,2,4 + MLPRender_Fea_late_view).  Same results as dynrf_static_app_fwd / dynrf_dyn_app_fwd
+ * (3-pass split TF32, fp32 accumulate).
+ * dynrf_pack_app_fwd: basis_mat weight [27][72 or 216], head layer-1 weight [128][138 | 135 | 107], layer-2 weight
+ *   [128][128] -> dynrf_app_fwd_wfloats(dynamic) packed floats.  head = DYNRF_HEAD_*.
+ * dynrf_app_fwd_tc: cst [dynrf_app_fwd_cst_floats()] = [b1(128) | b2(128) | W3[:, :128]^T (128x3) | W3[:, 128:131]^T (3x3, zeros
+ *   for DYNRF_HEAD_FEA) | b3(3)]; coords = lookup coordinates (xyz for the static field, xyz_prime for the dynamic one);
+ *   tfeat only for the dynamic field; featT (optional) [32][ld] receives the basis output of active sample j in column j. */
+int dynrf_app_fwd_wfloats(int dynamic);
+int dynrf_app_fwd_cst_floats(void);
+int dynrf_pack_app_fwd(int dynamic, int head, const float* basis_w, const float* w1, const float* w2, float* wq, void* stream);
+int dynrf_app_fwd_tc(const dynrf_field_cfg_t* cfg, int dynamic, const dynrf_vm_t* app, const float* wq, const float* cst,
+                     const float* rays, const float* xyz, const float* coords, const float* tfeat, int N, int S,
+                     const int32_t* active_idx, const int32_t* active_count, float* rgb, float* featT, int ld, void* stream);
+
 /* ---- tensor-core backward of the dynamic density + blending stage (reference: TensorBase.compute_densityfeature /
  * blending MLP backward reached through loss.backward() from train.py; forward at models/tensorBase.py density_layer*,
  * blending_layer*) -- both tables in one launch.

@@ -182,6 +182,21 @@ __device__ __forceinline__ float3 vm_group_bwd_agg(const float* __restrict__ pla
   return gx;
 }
 
+// Compile-time choice between the two scatters.  Measured on B200 (cfg2, synthetic rays, random-init fields): the L2
+// reduction units are NOT the limiter of any backward kernel (169 M red sectors in 3.3 ms), and the extra shuffles cost
+// 2-8 % -- so the plain scatter is the default.  Scenes with long coherent runs can flip this.
+constexpr bool kAggScatter = false;
+__device__ __forceinline__ float3 vm_group_bwd_w(const float* __restrict__ plane, const float* __restrict__ line,
+                                                 float* __restrict__ gplane, float* __restrict__ gline, int C, int W, const Tap1& tu,
+                                                 const Tap1& tv, const Tap1& tl, int c, float4 g, bool act, int lane) {
+  if constexpr (kAggScatter) {
+    return vm_group_bwd_agg(plane, line, gplane, gline, C, W, tu, tv, tl, c, g, act, lane);
+  } else {
+    if (!act) return make_float3(0.f, 0.f, 0.f);
+    return vm_group_bwd(plane, line, gplane, gline, C, W, tu, tv, tl, c, g);
+  }
+}
+
 // backward of gather_vm_rows: dA rows -> plane/line gradients; coordinate gradients are added to gxs[3][TM].
 template <int TM, int LD>
 __device__ __forceinline__ void scatter_vm_rows(const dynrf_vm_t& vm, const dynrf_vm_grad_t& gvm, const float (*xq)[TM],
@@ -205,7 +220,7 @@ __device__ __forceinline__ void scatter_vm_rows(const dynrf_vm_t& vm, const dynr
     for (int g = (part - q % NPART + NPART) % NPART; g < ng; g += NPART) {
       const float* a = dA + (size_t)(row_base + coff + g * 4) * LD + m;
       const float4 gg = make_float4(a[0], a[LD], a[2 * LD], a[3 * LD]);
-      const float3 r = vm_group_bwd_agg(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], C, vm.W[pl], tu, tv, tl, g * 4, gg, act,
+      const float3 r = vm_group_bwd_w(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], C, vm.W[pl], tu, tv, tl, g * 4, gg, act,
                                         tid & 31);
       gacc[u] += r.x;
       gacc[v] += r.y;

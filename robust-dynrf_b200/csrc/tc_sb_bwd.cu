@@ -295,7 +295,7 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
               const float* ll = tb ? vbl.line[0] : vden.line[0];
               float* gp = tb ? gbl.plane[0] : gden.plane[0];
               float* gl = tb ? gbl.line[0] : gden.line[0];
-              const float3 r = vm_group_bwd_agg(pp, ll, gp, gl, 16, G[0], load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 1, m, G[1]),
+              const float3 r = vm_group_bwd_w(pp, ll, gp, gl, 16, G[0], load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 1, m, G[1]),
                                                 load_tap1(taps, si, 2, m, G[2]), prt * 4, g4, act, lane);
               g0 += r.x;
               g1 += r.y;
@@ -310,13 +310,13 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
             float* gp = prt == 0 ? (tb ? gbl.plane[1] : gden.plane[1]) : (tb ? gbl.plane[2] : gden.plane[2]);
             float* gl = prt == 0 ? (tb ? gbl.line[1] : gden.line[1]) : (tb ? gbl.line[2] : gden.line[2]);
             if (prt == 0) {  // plane (x, z), line y
-              const float3 r = vm_group_bwd_agg(pp, ll, gp, gl, 4, G[0], load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 2, m, G[2]),
+              const float3 r = vm_group_bwd_w(pp, ll, gp, gl, 4, G[0], load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 2, m, G[2]),
                                                 load_tap1(taps, si, 1, m, G[1]), 0, g4, act, lane);
               g0 += r.x;
               g2 += r.y;
               g1 += r.z;
             } else {  // plane (y, z), line x
-              const float3 r = vm_group_bwd_agg(pp, ll, gp, gl, 4, G[1], load_tap1(taps, si, 1, m, G[1]), load_tap1(taps, si, 2, m, G[2]),
+              const float3 r = vm_group_bwd_w(pp, ll, gp, gl, 4, G[1], load_tap1(taps, si, 1, m, G[1]), load_tap1(taps, si, 2, m, G[2]),
                                                 load_tap1(taps, si, 0, m, G[0]), 0, g4, act, lane);
               g1 += r.x;
               g2 += r.y;

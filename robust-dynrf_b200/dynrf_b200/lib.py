@@ -14,7 +14,7 @@ PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # robust
 CSRC = os.path.join(PKG_ROOT, "csrc")
 LIB_DIR = os.path.join(PKG_ROOT, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdynrf_b200.so")
-SOURCES = ["ray_kernels.cu", "field_kernels.cu", "backward_kernels.cu", "selftest.cu", "tc_kernels.cu", "wgrad_gemm.cu", "tc_bwd_kernels.cu", "tc_sb_bwd.cu"]
+SOURCES = ["ray_kernels.cu", "field_kernels.cu", "backward_kernels.cu", "selftest.cu", "tc_kernels.cu", "wgrad_gemm.cu", "tc_bwd_kernels.cu", "tc_sb_bwd.cu", "tc_app_fwd.cu"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -116,6 +116,10 @@ PROTOTYPES = {
     "dynrf_head_bwd_cst_floats": [],
     "dynrf_pack_head_bwd": [_P, _P, _P, _P, _P],
     "dynrf_dyn_head_bwd_tc": [_cfg, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "dynrf_app_fwd_wfloats": [_I],
+    "dynrf_app_fwd_cst_floats": [],
+    "dynrf_pack_app_fwd": [_I, _I, _P, _P, _P, _P, _P],
+    "dynrf_app_fwd_tc": [_cfg, _I, _vm, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P],
     "dynrf_sb_bwd_wfloats": [],
     "dynrf_pack_sb_bwd": [_P, _P, _P, _P, _P],
     "dynrf_dyn_mlp_bwd_tc": [_cfg, _vm, _vm, _vg, _vg, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
@@ -132,7 +136,7 @@ PROTOTYPES = {
 }
 
 _lib = None
-_NO_LAUNCH = {"dynrf_abi_version", "dynrf_pad_k", "dynrf_pad_n", "dynrf_strerror", "dynrf_sb_umma_floats", "dynrf_head_bwd_wfloats", "dynrf_head_bwd_cst_floats", "dynrf_sb_bwd_wfloats"}
+_NO_LAUNCH = {"dynrf_abi_version", "dynrf_pad_k", "dynrf_pad_n", "dynrf_strerror", "dynrf_sb_umma_floats", "dynrf_head_bwd_wfloats", "dynrf_head_bwd_cst_floats", "dynrf_sb_bwd_wfloats", "dynrf_app_fwd_wfloats", "dynrf_app_fwd_cst_floats"}
 
 # every other entry point enqueues exactly one kernel of this library; bench.py reports the count
 launch_count = 0

@@ -201,6 +201,43 @@ class PackedSigmaBlend:
         return self
 
 
+class PackedAppFwd:
+    """Operands of dynrf_app_fwd_tc for one field: packed split-TF32 weights (basis_mat, head layers 1-2) and the
+    constant block [b1 | b2 | W3[:, :128]^T | W3[:, 128:131]^T (zeros without a late view input) | b3]."""
+
+    def __init__(self, m):
+        self.m = m
+        lib = L.load()
+        dev = m.basis_mat.weight.device
+        self.dyn = 1 if m.is_dynamic else 0
+        self.wq = torch.empty(lib.dynrf_app_fwd_wfloats(self.dyn), device=dev)
+        self.cst = torch.empty(lib.dynrf_app_fwd_cst_floats(), device=dev)
+        self._key = None
+
+    def refresh(self):
+        m = self.m
+        tbl = m._layer_table()
+        l1, l2, l3 = tbl["h1"], tbl["h2"], tbl["h3"]
+        ps = [m.basis_mat.weight, l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias]
+        key = (PARAM_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self._key:
+            with torch.no_grad():
+                L.check(L.load().dynrf_pack_app_fwd(self.dyn, m.head_mode, _p(_f32c(ps[0].detach())), _p(_f32c(ps[1].detach())),
+                                                    _p(_f32c(ps[3].detach())), _p(self.wq), _stream()), "dynrf_pack_app_fwd")
+                w3 = l3.weight.detach()
+                w3v = w3[:, 128:131].t().reshape(-1) if w3.shape[1] == 131 else torch.zeros(9, device=w3.device)
+                torch.cat((l1.bias.detach(), l2.bias.detach(), w3[:, :128].t().reshape(-1), w3v, l3.bias.detach()), out=self.cst)
+            self._key = key
+        return self
+
+
+def packed_app_fwd(m) -> PackedAppFwd:
+    p = m.__dict__.get("_packed_app_fwd")
+    if p is None:
+        p = m.__dict__["_packed_app_fwd"] = PackedAppFwd(m)
+    return p.refresh()
+
+
 def field_cfg(aabb: torch.Tensor, near_far, distance_scale, weight_thres, act: str, density_shift, ray_type: str) -> L.FieldCfgT:
     a = aabb.detach().cpu().tolist()
     cfg = L.FieldCfgT()
@@ -290,6 +327,12 @@ def static_app_raw(m, st, ray_type):
     cfg = m.native_cfg(ray_type)
     n, s = st["sigma"].shape
     vapp = vm_struct(m.app_plane, m.app_line)
+    if USE_TC:
+        pa = packed_app_fwd(m)
+        L.check(lib.dynrf_app_fwd_tc(C.byref(cfg), 0, C.byref(vapp), _p(pa.wq), _p(pa.cst), _p(st["rays"]), _p(st["xyz"]), _p(st["xyz"]),
+                                     None, n, s, _p(st["idx"]), _p(st["cnt"]), _p(st["rgb"]), _p(st.get("featT")), st.get("ldf", 0),
+                                     _stream()), "dynrf_app_fwd_tc")
+        return
     ly = m.packed_layers()
     L.check(lib.dynrf_static_app_fwd(C.byref(cfg), C.byref(vapp), C.byref(ly["basis"]), C.byref(ly["h1"]), C.byref(ly["h2"]),
                                      C.byref(ly["h3"]), m.head_mode, _p(st["rays"]), _p(st["xyz"]), n, s, _p(st["idx"]),
@@ -351,9 +394,14 @@ def dynamic_forward_raw(m, rays, ts, xyz, z_vals, valid, ray_type, save_feat=Fal
     vapp = vm_struct(m.app_plane, m.app_line)
     ldf = round_up(n * s, 128)
     featT = torch.empty(32, ldf, device=dev) if save_feat else None  # basis outputs, kept for the tensor-core backward
-    L.check(lib.dynrf_dyn_app_fwd(C.byref(cfg), C.byref(vapp), C.byref(ly["basis"]), C.byref(ly["h1"]), C.byref(ly["h2"]),
-                                  C.byref(ly["h3"]), _p(rays), _p(xyz), _p(xyz_prime), _p(tfeat), n, s, _p(idx), _p(cnt),
-                                  _p(rgb), _p(featT), ldf, _stream()), "dynrf_dyn_app_fwd")
+    if USE_TC:
+        pa = packed_app_fwd(m)
+        L.check(lib.dynrf_app_fwd_tc(C.byref(cfg), 1, C.byref(vapp), _p(pa.wq), _p(pa.cst), _p(rays), _p(xyz), _p(xyz_prime), _p(tfeat),
+                                     n, s, _p(idx), _p(cnt), _p(rgb), _p(featT), ldf, _stream()), "dynrf_app_fwd_tc")
+    else:
+        L.check(lib.dynrf_dyn_app_fwd(C.byref(cfg), C.byref(vapp), C.byref(ly["basis"]), C.byref(ly["h1"]), C.byref(ly["h2"]),
+                                      C.byref(ly["h3"]), _p(rays), _p(xyz), _p(xyz_prime), _p(tfeat), n, s, _p(idx), _p(cnt),
+                                      _p(rgb), _p(featT), ldf, _stream()), "dynrf_dyn_app_fwd")
     return dict(sigma=sigma, blend=blend, weight=weight, dists=dists, rgb=rgb, xyz_prime=xyz_prime, tfeat=tfeat, idx=idx,
                 cnt=cnt, rays=rays, ts=ts, xyz=xyz, z_vals=z_vals, valid=valid_u8, featT=featT, ldf=ldf)
 
