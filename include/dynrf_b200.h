@@ -263,20 +263,25 @@ int dynrf_dyn_sigma_blend_fwd_tc2(const dynrf_field_cfg_t* cfg, const dynrf_vm_t
                                   const float* xyz, const float* xyz_prime, const uint8_t* valid, const float* tfeat, int N,
                                   int S, float* sigma, float* blend, void* stream);
 
-/* ---- tensor-core backward of the dynamic appearance head (late-view MLP on the active samples) -----------
- * dynrf_pack_head_bwd: layer-1 [128][107] / layer-2 [128][128] weights -> dynrf_head_bwd_wfloats() packed floats + the column
- *   map [113] of X1T rows to nn.Linear input columns (-1: padding row, -2: the ones row whose gradient column is d bias).
- * dynrf_dyn_head_bwd_tc: cst = [b1(128) | b2(128) | W3[:, :128]^T (128x3) | W3[:, 128:131]^T (3x3) | b3(3)];
- *   writes feature-major [rows][ld] tensors X1T[113] H1T[128] H2T[128] DH2T[128] DH1T[128] DOT[3] DFT[32] (column j = j-th
- *   active sample) and accumulates gw3v [3][3] (d W3[:, 128+k]) and gb3 [3].  ld >= round_up(N*S,128), multiple of 4.
+/* ---- tensor-core backward of the appearance head on the active samples -----------------------------------
+ * dynamic = 1: MLPRender_Fea_late_view of the dynamic field; dynamic = 0: MLPRender_Fea / MLPRender_Fea_TimeEmbedding of the
+ *   static field (reference models/tensorBase.py MLPRender_Fea*, gradients reached through loss.backward()).
+ * dynrf_pack_head_bwd: layer-1 [128][107 | 138 | 135] / layer-2 [128][128] weights -> dynrf_head_bwd_wfloats(dynamic) packed
+ *   floats + the column map [dynrf_head_bwd_xrows(dynamic)] of X1T rows to nn.Linear input columns (-1: padding row, -2: the
+ *   ones row whose gradient column is d bias).
+ * dynrf_head_bwd_tc: cst = [b1(128) | b2(128) | W3[:, :128]^T (128x3) | W3[:, 128:131]^T (3x3, zeros for DYNRF_HEAD_FEA) | b3(3)];
+ *   featT [32][ld] = basis outputs saved by dynrf_app_fwd_tc; writes feature-major [rows][ld] tensors X1T[xrows] H1T[128]
+ *   H2T[128] DH2T[128] DH1T[128] DOT[3] DFT[32] (column j = j-th active sample) and accumulates gw3v [3][3] (d W3[:, 128+k]),
+ *   gb3 [3] and (static MLP_Fea head, optional) gviewdir [N][3].  ld >= round_up(N*S,128), multiple of 4.
  * dynrf_basis_bwd: DFT -> packed basis gradient [K][32] (+=), plane / line gradients (+=), d loss / d coords (+=). */
-int dynrf_head_bwd_wfloats(void);
+int dynrf_head_bwd_wfloats(int dynamic);
 int dynrf_head_bwd_cst_floats(void);
-int dynrf_pack_head_bwd(const float* w1, const float* w2, float* wq, int32_t* colmap, void* stream);
-int dynrf_dyn_head_bwd_tc(const dynrf_field_cfg_t* cfg, const float* wq, const float* cst, const float* rays, const float* xyz,
-                          const float* tfeat, const float* featT, const float* grgb, const int32_t* active_idx,
-                          const int32_t* active_count, int N, int S, int ld, float* X1T, float* H1T, float* H2T, float* DH2T,
-                          float* DH1T, float* DOT, float* DFT, float* gw3v, float* gb3, void* stream);
+int dynrf_head_bwd_xrows(int dynamic);
+int dynrf_pack_head_bwd(int dynamic, int head, const float* w1, const float* w2, float* wq, int32_t* colmap, void* stream);
+int dynrf_head_bwd_tc(const dynrf_field_cfg_t* cfg, int dynamic, const float* wq, const float* cst, const float* rays, const float* xyz,
+                      const float* tfeat, const float* featT, const float* grgb, const int32_t* active_idx,
+                      const int32_t* active_count, int N, int S, int ld, float* X1T, float* H1T, float* H2T, float* DH2T,
+                      float* DH1T, float* DOT, float* DFT, float* gw3v, float* gb3, float* gviewdir, void* stream);
 int dynrf_basis_bwd(const dynrf_field_cfg_t* cfg, int dynamic, const dynrf_vm_t* app, const dynrf_vm_grad_t* gapp, const float* wbB,
                     const float* coords, const float* DFT, int ld, int N, int S, const int32_t* active_idx,
                     const int32_t* active_count, float* gbasis_wt, float* gcoord, void* stream);

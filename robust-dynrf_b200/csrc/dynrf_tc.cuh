@@ -135,6 +135,7 @@ struct Ring {
   float* wbuf;         // 2 x kWSlotFloats
   uint32_t chunk;      // running chunk counter, identical in every thread
   uint32_t tmem;
+  uint32_t wslot = kWSlotFloats;  // floats per weight slot
 };
 
 __device__ __forceinline__ void ring_wait_free(const Ring& r) {
@@ -150,7 +151,7 @@ __device__ __forceinline__ void ring_prefetch_w(const Ring& r, uint32_t c, const
     umma::mbar_wait(&r.bar_free[pc % 3], (pc / 3) & 1);
   }
   mbar_expect_tx(&r.bar_w[c & 1], bytes);
-  tma_load_1d(r.wbuf + (size_t)(c & 1) * kWSlotFloats, blob, bytes, &r.bar_w[c & 1]);
+  tma_load_1d(r.wbuf + (size_t)(c & 1) * r.wslot, blob, bytes, &r.bar_w[c & 1]);
 }
 
 // tid 0: wait for this chunk's weights, issue the 3-pass MMAs, commit to the operand buffer's barrier
@@ -161,7 +162,7 @@ __device__ __forceinline__ void ring_issue(const Ring& r, int rows, uint32_t col
   umma::fence_after_sync();
   const uint32_t idesc = umma::make_idesc_tf32(kTileM, N);
   const uint32_t sa_hi = umma::smem_u32(r.abuf + (size_t)(c % 3) * kOpFloats), sa_lo = sa_hi + kOpLo * 4;
-  const uint32_t sb_hi = umma::smem_u32(r.wbuf + (size_t)(c & 1) * kWSlotFloats), sb_lo = sb_hi + N * rows * 4;
+  const uint32_t sb_hi = umma::smem_u32(r.wbuf + (size_t)(c & 1) * r.wslot), sb_lo = sb_hi + N * rows * 4;
 #pragma unroll
   for (int ps = 0; ps < 3; ++ps) {
     const uint32_t sa = (ps == 2) ? sa_lo : sa_hi;

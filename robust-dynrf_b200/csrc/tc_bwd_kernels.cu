@@ -15,32 +15,54 @@
 
 namespace dynrf {
 
-constexpr int kHbChunks = 16;
-__host__ __device__ constexpr int hb_rows(int j) { return j == 2 ? 16 : 32; }
-__host__ __device__ constexpr int hb_n(int j) { return j < 12 ? 128 : 32; }
-__host__ __device__ constexpr int hb_woff(int j) {
-  int o = 0;
-  for (int i = 0; i < j; ++i) o += 2 * hb_n(i) * hb_rows(i);
-  return o;
+__device__ __forceinline__ void tmem_ld8_(uint32_t taddr, float (&r)[8]) {
+  uint32_t u[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
 }
-constexpr int kHbWFloats = hb_woff(kHbChunks);
+
+// chunk schedule.  L1 chunks (DYN: 3 position/time + 1 feature; static: 4 encoding + 1 feature/viewdir), 4 L2 chunks,
+// 4 chunks of dH1 = dH2 W2 and 4 chunks of the layer-1 data gradient (DYN: the 27 feature columns, N = 32; static: all
+// 160 operand rows, N = 160, because the gradient also flows through the sin / cos encodings of the features).
+template <bool DYN>
+struct HeadBwd {
+  static constexpr int kNL1 = DYN ? 4 : 5;
+  static constexpr int kChunks = kNL1 + 12;
+  static constexpr int kN4 = DYN ? 32 : 160;
+  static constexpr int kXRows = DYN ? 113 : 161;  // X1T rows (last = ones)
+  __host__ __device__ static constexpr int rows(int j) { return (DYN && j == 2) ? 16 : 32; }
+  __host__ __device__ static constexpr int n(int j) { return j < kNL1 + 8 ? 128 : kN4; }
+  __host__ __device__ static constexpr int woff(int j) {
+    int o = 0;
+    for (int i = 0; i < j; ++i) o += 2 * n(i) * rows(i);
+    return o;
+  }
+  static constexpr int kWFloats = woff(kChunks);
+};
+constexpr int kHbWSlot = 2 * 160 * kKC;  // floats per weight slot (largest chunk: N = 160)
 
 // constants in shared memory: b1[128] | b2[128] | W3t[128][3] | W3v[3][3] | b3[3]
 constexpr int kHbCst = 128 + 128 + 384 + 9 + 3;
 
 struct HeadBwdArgs {
-  const float* wq;      // kHbWFloats: packed split weights for the 16 chunks
+  const float* wq;      // packed split weights for the chunks
   const float* cst;     // kHbCst
   const float* rays;    // [N][6]
   const float* xyz;     // [N*S][3]
-  const float* tfeat;   // [N][48]
+  const float* tfeat;   // [N][48] (dynamic head)
   const float* featT;   // [32][ld] basis output saved by the forward (rows 27..31 zero)
   const float* grgb;    // [N*S][3]
   const int32_t* active_idx;
   const int32_t* active_count;
   int S, ld;
   // feature-major outputs, row stride ld
-  float* X1T;   // [113]: 80 position/time rows (this kernel's K order) | 32 feat rows | 1 row of ones
+  float* X1T;   // dynamic [113]: 80 position/time rows (this kernel's K order) | 32 feat rows | ones
+                // static  [161]: 4 x 32 encoding rows | 27 feat + 3 viewdir + 2 zero rows | ones
   float* H1T;   // [128]
   float* H2T;   // [128]
   float* DH2T;  // [128]
@@ -49,16 +71,20 @@ struct HeadBwdArgs {
   float* DFT;   // [32]
   float* gw3v;  // [3][3] += d W3[:, 128+k]   (row c, col k)
   float* gb3;   // [3]    += d b3
+  float* gvd;   // [N][3] += d loss / d viewdir through layer 1 (static MLP_Fea head, optional)
 };
 
-constexpr size_t kHbSmem = (size_t)(3 * kOpFloats + 2 * kWSlotFloats + kHbCst + 4 * 3 * kTileM + 3 * kTileM) * sizeof(float) +
+constexpr size_t kHbSmem = (size_t)(3 * kOpFloats + 2 * kHbWSlot + kHbCst + 4 * 3 * kTileM + 3 * kTileM) * sizeof(float) +
                            sizeof(TileScratch<kTileM>) + 128;
 
+template <bool DYN>
 __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_t cfg, HeadBwdArgs a) {
+  using HB = HeadBwd<DYN>;
+  constexpr int kL2 = HB::kNL1, kD2 = HB::kNL1 + 4, kD1 = HB::kNL1 + 8;  // first chunk of each group
   extern __shared__ __align__(128) float smem[];
   float* abuf = smem;
   float* wbuf = abuf + 3 * kOpFloats;
-  float* cst = wbuf + 2 * kWSlotFloats;
+  float* cst = wbuf + 2 * kHbWSlot;
   float* part = cst + kHbCst;       // [4][3][128] partial output dots
   float* go = part + 4 * 3 * kTileM;  // [3][128] d loss / d (pre-sigmoid output)
   TileScratch<kTileM>& scr = *reinterpret_cast<TileScratch<kTileM>*>(go + 3 * kTileM);
@@ -78,11 +104,11 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  Ring ring{bar_free, bar_w, abuf, wbuf, 0u, *tslot};
+  Ring ring{bar_free, bar_w, abuf, wbuf, 0u, *tslot, (uint32_t)kHbWSlot};
   const int count = *a.active_count;
   const int ntiles = (count + kTileM - 1) / kTileM;
   const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const uint32_t total_chunks = (uint32_t)my_tiles * kHbChunks;
+  const uint32_t total_chunks = (uint32_t)my_tiles * HB::kChunks;
   const float* b1 = cst;
   const float* b2 = cst + 128;
   const float* W3t = cst + 256;   // [128][3]
@@ -92,18 +118,19 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
   if (warp == kProdThreads / 32) {
     // ===================== tensor-core warp =====================
     if (lane == 0 && total_chunks > 0) {
-      ring_prefetch_w(ring, 0, a.wq + hb_woff(0), 2u * hb_n(0) * hb_rows(0) * 4u);
+      ring_prefetch_w(ring, 0, a.wq + HB::woff(0), 2u * HB::n(0) * HB::rows(0) * 4u);
       for (uint32_t c = 0; c < total_chunks; ++c) {
-        const int j = (int)(c % kHbChunks);
+        const int j = (int)(c % HB::kChunks);
         ring.chunk = c;
         umma::mbar_wait(&bar_full[c % 3], (c / 3) & 1);
-        const uint32_t col0 = j < 4 ? 0u : (j < 8 ? 128u : (j < 12 ? 256u : 384u));
-        const bool first = (j == 0) || (j == 4) || (j == 8) || (j == 12);
-        if (j < 12) ring_issue<128>(ring, hb_rows(j), col0, first);
-        else ring_issue<32>(ring, hb_rows(j), col0, first);
+        if (j < kL2) ring_issue<128>(ring, HB::rows(j), 0u, j == 0);
+        else if (j < kD2) ring_issue<128>(ring, 32, 128u, j == kL2);
+        else if (j < kD1) ring_issue<128>(ring, 32, 256u, j == kD2);
+        else if (DYN) ring_issue<32>(ring, 32, 384u, j == kD1);
+        else ring_issue<160>(ring, 32, 0u, j == kD1);  // acc1 / acc2 are dead by now (see epilogue 3)
         if (c + 1 < total_chunks) {
-          const int nj = (j + 1) % kHbChunks;
-          ring_prefetch_w(ring, c + 1, a.wq + hb_woff(nj), 2u * hb_n(nj) * hb_rows(nj) * 4u);
+          const int nj = (j + 1) % HB::kChunks;
+          ring_prefetch_w(ring, c + 1, a.wq + HB::woff(nj), 2u * HB::n(nj) * HB::rows(nj) * 4u);
         }
       }
     }
@@ -111,7 +138,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
   } else {
     // ===================== producer / epilogue warps =====================
     const int m = tid & (kTileM - 1), prt = tid >> 7;
-    const int q = warp & 3, cb = warp >> 2;  // TMEM lane quadrant, 32-column block
+    const int q = warp & 3, cb = warp >> 2;  // TMEM lane quadrant, 32-column block   (m == q * 32 + lane, prt == cb)
     const int em = q * 32 + lane;            // sample row this thread owns in the epilogues
     const AabbNorm nb = make_norm(cfg);
     const int ld = a.ld;
@@ -152,33 +179,80 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
       }
       prod_bar();
       const uint32_t base = ring.chunk;
-      // ---- L1 operand: 3 position/time chunks (also streamed to X1T rows 0..79) + the feat chunk (X1T rows 80..111 <- featT)
+      float f[8];  // static head: this thread's 8 basis outputs (features 8 cb .. 8 cb + 7), kept for epilogue 4
+      if (DYN) {
+        // ---- L1 operand: 3 position/time chunks (also streamed to X1T rows 0..79) + the feat chunk (X1T rows 80..111 <- featT)
 #pragma unroll 1
-      for (int j = 0; j < 3; ++j) {
-        ring_wait_free(ring);
-        float* buf = ring_abuf(ring);
-        const int u0 = j * 5, nu = (j == 2) ? 4 : 5;
-        for (int u = prt; u < nu; u += 4) produce_pos_unit(u0 + u, scr, a.tfeat, m, buf, a.X1T + (size_t)(j * 32) * ld, ld, jg0 + m);
-        arrive();
-      }
-      {
-        ring_wait_free(ring);
-        float* buf = ring_abuf(ring);
-        const bool on = scr.on[m] != 0;
-        for (int qq = prt; qq < 8; qq += 4) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (on) {
-            const float* f = a.featT + (size_t)(qq * 4) * ld + jg0 + m;
-            v = make_float4(__ldg(f), __ldg(f + ld), __ldg(f + 2 * (size_t)ld), __ldg(f + 3 * (size_t)ld));
-          }
-          store_quad(buf, m, qq, v);
-          store_quad_g(a.X1T, ld, 80 + qq * 4, jg0 + m, v);
+        for (int j = 0; j < 3; ++j) {
+          ring_wait_free(ring);
+          float* buf = ring_abuf(ring);
+          const int u0 = j * 5, nu = (j == 2) ? 4 : 5;
+          for (int u = prt; u < nu; u += 4) produce_pos_unit(u0 + u, scr, a.tfeat, m, buf, a.X1T + (size_t)(j * 32) * ld, ld, jg0 + m);
+          arrive();
         }
-        if (prt == 0) a.X1T[(size_t)112 * ld + jg0 + m] = on ? 1.f : 0.f;  // ones row: its weight-gradient column is d b1
+        {
+          ring_wait_free(ring);
+          float* buf = ring_abuf(ring);
+          const bool on = scr.on[m] != 0;
+          for (int qq = prt; qq < 8; qq += 4) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (on) {
+              const float* fp = a.featT + (size_t)(qq * 4) * ld + jg0 + m;
+              v = make_float4(__ldg(fp), __ldg(fp + ld), __ldg(fp + 2 * (size_t)ld), __ldg(fp + 3 * (size_t)ld));
+            }
+            store_quad(buf, m, qq, v);
+            store_quad_g(a.X1T, ld, 80 + qq * 4, jg0 + m, v);
+          }
+          if (prt == 0) a.X1T[(size_t)112 * ld + jg0 + m] = on ? 1.f : 0.f;  // ones row: its weight-gradient column is d b1
+          arrive();
+        }
+      } else {
+        // ---- L1 operand: 4 encoding chunks (chunk c <- warps with cb == c) + the [features | viewdir] chunk; X1T rows 0..159
+        const bool on = scr.on[em] != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = on ? __ldg(a.featT + (size_t)(cb * 8 + i) * ld + jg0 + em) : 0.f;
+#pragma unroll 1
+        for (int c4 = 0; c4 < 4; ++c4) {
+          ring_wait_free(ring);
+          if (c4 == cb) {
+            float* buf = ring_abuf(ring);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {   // frequency 1, 2
+              float sv[8], cv[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) sincosf(h ? f[i] * 2.0f : f[i], &sv[i], &cv[i]);
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const float4 s4 = make_float4(sv[half * 4], sv[half * 4 + 1], sv[half * 4 + 2], sv[half * 4 + 3]);
+                const float4 c4v = make_float4(cv[half * 4], cv[half * 4 + 1], cv[half * 4 + 2], cv[half * 4 + 3]);
+                store_quad(buf, em, h * 2 + half, s4);
+                store_quad(buf, em, 4 + h * 2 + half, c4v);
+                store_quad_g(a.X1T, ld, cb * 32 + (h * 2 + half) * 4, jg0 + em, s4);
+                store_quad_g(a.X1T, ld, cb * 32 + (4 + h * 2 + half) * 4, jg0 + em, c4v);
+              }
+            }
+          }
+          arrive();
+        }
+        ring_wait_free(ring);
+        {
+          float* buf = ring_abuf(ring);
+          float4 v0 = make_float4(f[0], f[1], f[2], f[3]), v1 = make_float4(f[4], f[5], f[6], f[7]);
+          if (cb == 3) {  // rows 27..29: view direction (zero weights for the time-embedding head)
+            v0.w = on ? scr.xu[0][em] : 0.f;
+            v1.x = on ? scr.xu[1][em] : 0.f;
+            v1.y = on ? scr.xu[2][em] : 0.f;
+          }
+          store_quad(buf, em, cb * 2, v0);
+          store_quad(buf, em, cb * 2 + 1, v1);
+          store_quad_g(a.X1T, ld, 128 + cb * 8, jg0 + em, v0);
+          store_quad_g(a.X1T, ld, 128 + cb * 8 + 4, jg0 + em, v1);
+          if (cb == 0) a.X1T[(size_t)160 * ld + jg0 + em] = on ? 1.f : 0.f;
+        }
         arrive();
       }
       // ---- epilogue 1: h1 = relu(acc1 + b1) -> L2 operand chunk cb, H1T
-      wait_chunk(base + 3);
+      wait_chunk(base + kL2 - 1);
       {
         float r[32];
         umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 32, r);
@@ -203,7 +277,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
         }
       }
       // ---- epilogue 2: h2 = relu(acc2 + b2); output layer; d(out); dH2 -> dgrad-2 operand chunk cb
-      wait_chunk(base + 7);
+      wait_chunk(base + kD2 - 1);
       {
         float h2[32];
         umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + 128 + cb * 32, h2);
@@ -253,8 +327,6 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
         }
 #pragma unroll 1
         for (int c4 = 0; c4 < 4; ++c4) {
-          // every warp waits for the slot's previous use before arriving: an early arrival meant for chunk c would
-          // otherwise be counted in the still-open phase of chunk c-3 on the same barrier
           ring_wait_free(ring);
           if (c4 == cb) {
             float* buf = ring_abuf(ring);
@@ -268,47 +340,78 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
           arrive();
         }
       }
-      // ---- epilogue 3: dH1 = acc3 * [h1 > 0] -> dgrad-1 operand chunk cb, DH1T
-      wait_chunk(base + 11);
+      // ---- epilogue 3: dH1 = acc3 * [h1 > 0] -> dgrad-1 operand chunk cb, DH1T.  All TMEM reads (acc3 and the sign of
+      // acc1) finish before any warp arrives on the first dgrad-1 chunk: the static head's dgrad-1 GEMM overwrites acc1 / acc2.
+      wait_chunk(base + kD1 - 1);
       {
+        float r3[32];
+        const bool on = scr.on[em] != 0;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float t3[16], t1[16];
+          umma::tmem_ld16(ring.tmem + ((uint32_t)(q * 32) << 16) + 256 + cb * 32 + hf * 16, t3);
+          umma::tmem_ld16(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 32 + hf * 16, t1);
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) r3[hf * 16 + jj] = (on && (t1[jj] + b1[cb * 32 + hf * 16 + jj]) > 0.f) ? t3[jj] : 0.f;
+        }
+        umma::fence_before_sync();
+        prod_bar();
 #pragma unroll 1
         for (int c4 = 0; c4 < 4; ++c4) {
-          // every warp waits for the slot's previous use before arriving: an early arrival meant for chunk c would
-          // otherwise be counted in the still-open phase of chunk c-3 on the same barrier
           ring_wait_free(ring);
           if (c4 == cb) {
             float* buf = ring_abuf(ring);
-            const bool on = scr.on[em] != 0;
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              float r3[16], r1[16];
-              umma::tmem_ld16(ring.tmem + ((uint32_t)(q * 32) << 16) + 256 + cb * 32 + hf * 16, r3);
-              umma::tmem_ld16(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 32 + hf * 16, r1);
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) r3[jj] = (on && (r1[jj] + b1[cb * 32 + hf * 16 + jj]) > 0.f) ? r3[jj] : 0.f;
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq) {
-                const float4 v = make_float4(r3[qq * 4], r3[qq * 4 + 1], r3[qq * 4 + 2], r3[qq * 4 + 3]);
-                store_quad(buf, em, hf * 4 + qq, v);
-                store_quad_g(a.DH1T, ld, cb * 32 + hf * 16 + qq * 4, jg0 + em, v);
-              }
+            for (int qq = 0; qq < 8; ++qq) {
+              const float4 v = make_float4(r3[qq * 4], r3[qq * 4 + 1], r3[qq * 4 + 2], r3[qq * 4 + 3]);
+              store_quad(buf, em, qq, v);
+              store_quad_g(a.DH1T, ld, cb * 32 + qq * 4, jg0 + em, v);
             }
           }
           arrive();
         }
       }
       // ---- epilogue 4: dfeat
-      wait_chunk(base + 15);
-      if (cb == 0) {
-        float r4[32];
-        umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + 384, r4);
+      wait_chunk(base + HB::kChunks - 1);
+      if (DYN) {
+        if (cb == 0) {
+          float r4[32];
+          umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + 384, r4);
 #pragma unroll
-        for (int qq = 0; qq < 8; ++qq) {
-          float4 v = make_float4(r4[qq * 4], r4[qq * 4 + 1], r4[qq * 4 + 2], r4[qq * 4 + 3]);
-          if (qq == 6) v.w = 0.f;            // only 27 feature rows carry a gradient
-          if (qq == 7) v = make_float4(0.f, 0.f, 0.f, 0.f);
-          store_quad_g(a.DFT, ld, qq * 4, jg0 + em, v);
+          for (int qq = 0; qq < 8; ++qq) {
+            float4 v = make_float4(r4[qq * 4], r4[qq * 4 + 1], r4[qq * 4 + 2], r4[qq * 4 + 3]);
+            if (qq == 6) v.w = 0.f;            // only 27 feature rows carry a gradient
+            if (qq == 7) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            store_quad_g(a.DFT, ld, qq * 4, jg0 + em, v);
+          }
         }
+      } else {
+        // dX columns: [32 cb, 32 cb + 32) = d(sin f, sin 2f, cos f, cos 2f) of this thread's 8 features, [128 + 8 cb, +8) = d f
+        float dx[32], df[8];
+        umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 32, dx);
+        tmem_ld8_(ring.tmem + ((uint32_t)(q * 32) << 16) + 128 + cb * 8, df);
+        const bool on = scr.on[em] != 0;
+        if (cb == 3 && on && a.gvd) {
+          const int ry = scr.ray[em];
+          atomicAdd(a.gvd + (size_t)ry * 3 + 0, df[3]);
+          atomicAdd(a.gvd + (size_t)ry * 3 + 1, df[4]);
+          atomicAdd(a.gvd + (size_t)ry * 3 + 2, df[5]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float s1, c1, s2, c2;
+          sincosf(f[i], &s1, &c1);
+          sincosf(f[i] * 2.0f, &s2, &c2);
+          // d/df [sin f, sin 2f, cos f, cos 2f] = [cos f, 2 cos 2f, -sin f, -2 sin 2f]
+          float g = df[i];
+          g = fmaf(dx[i], c1, g);
+          g = fmaf(dx[8 + i], 2.0f * c2, g);
+          g = fmaf(dx[16 + i], -s1, g);
+          g = fmaf(dx[24 + i], -2.0f * s2, g);
+          df[i] = (on && cb * 8 + i < 27) ? g : 0.f;
+        }
+        store_quad_g(a.DFT, ld, cb * 8, jg0 + em, make_float4(df[0], df[1], df[2], df[3]));
+        store_quad_g(a.DFT, ld, cb * 8 + 4, jg0 + em, make_float4(df[4], df[5], df[6], df[7]));
       }
       umma::fence_before_sync();
       prod_bar();
@@ -327,45 +430,73 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
 
 // ------------------------------------------------------------------------------------------------
 // weight packing for k_head_bwd_tc: chunk j holds B[row r < N_j][k < rows_j] (split hi | lo, K-major):
-//   j 0..2   L1, position/time inputs : B[n][k] = W1[n][27 + p(j,k)]         (p: this kernel's K order -> reference order)
-//   j 3      L1, feat inputs          : B[n][k] = W1[n][k] (k < 27)
-//   j 4..7   L2                       : B[n][k] = W2[n][32 (j-4) + k]
-//   j 8..11  dH1 = dH2 W2             : B[kin][nn] = W2[32 (j-8) + nn][kin]
-//   j 12..15 dfeat = dH1 W1[:, feat]  : B[f][nn] = W1[32 (j-12) + nn][f] (f < 27)
+//   L1 chunks   : B[n][k] = W1[n][col(j, k)]   (col: this kernel's K order -> nn.Linear input column, -1 = zero row)
+//   L2 chunks   : B[n][k] = W2[n][32 jj + k]
+//   dgrad-2     : B[kin][nn] = W2[32 jj + nn][kin]                     (dH1 = dH2 W2)
+//   dgrad-1     : B[r][nn] = W1[32 jj + nn][col of operand row r]      (dynamic: r < 27 feature columns; static: all 160 rows)
 
-__global__ void k_pack_head_bwd(const float* __restrict__ w1 /*[128][107]*/, const float* __restrict__ w2 /*[128][128]*/,
+template <bool DYN>
+__device__ __forceinline__ int head_l1_col(int r, int head) {  // operand row r of layer 1 -> nn.Linear input column (-1: none)
+  if (DYN) {
+    if (r < 80) return 27 + pos_src_index(r);
+    return (r - 80) < 27 ? (r - 80) : -1;
+  }
+  const int sin0 = head == DYNRF_HEAD_FEA ? 30 : 27, cos0 = sin0 + 54;
+  if (r < 128) {
+    const int c = r >> 5, k = r & 31;
+    const int qd = k >> 2, el = k & 3;
+    const int trig = qd >> 2, fq = (qd >> 1) & 1, d = c * 8 + (qd & 1) * 4 + el;
+    return d < 27 ? (trig ? cos0 : sin0) + d * 2 + fq : -1;
+  }
+  const int k = r - 128;
+  if (k < 27) return k;
+  if (k < 30 && head == DYNRF_HEAD_FEA) return k;
+  return -1;
+}
+
+template <bool DYN>
+__global__ void k_pack_head_bwd(const float* __restrict__ w1, int K1, const float* __restrict__ w2 /*[128][128]*/, int head,
                                 float* __restrict__ wq) {
+  using HB = HeadBwd<DYN>;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= kHbWFloats / 2) return;
+  if (i >= HB::kWFloats / 2) return;
   int j = 0, base = 0;
-  for (; j < kHbChunks; ++j) {
-    const int sz = hb_n(j) * hb_rows(j);
+  for (; j < HB::kChunks; ++j) {
+    const int sz = HB::n(j) * HB::rows(j);
     if (i < base + sz) break;
     base += sz;
   }
-  const int N = hb_n(j), rows = hb_rows(j);
+  const int N = HB::n(j), rows = HB::rows(j);
   const int e = i - base;
   const int r = e / rows, k = e % rows;
   float v = 0.f;
-  if (j < 3) v = __ldg(w1 + (size_t)r * 107 + 27 + pos_src_index(j * 32 + k));
-  else if (j == 3) v = k < 27 ? __ldg(w1 + (size_t)r * 107 + k) : 0.f;
-  else if (j < 8) v = __ldg(w2 + (size_t)r * 128 + 32 * (j - 4) + k);
-  else if (j < 12) v = __ldg(w2 + (size_t)(32 * (j - 8) + k) * 128 + r);
-  else v = r < 27 ? __ldg(w1 + (size_t)(32 * (j - 12) + k) * 107 + r) : 0.f;
+  if (j < HB::kNL1) {
+    const int col = head_l1_col<DYN>(((DYN && j == 3) ? 80 : j * 32) + k, head);   // the dynamic head's third chunk has 16 rows
+    if (col >= 0) v = __ldg(w1 + (size_t)r * K1 + col);
+  } else if (j < HB::kNL1 + 4) {
+    v = __ldg(w2 + (size_t)r * 128 + 32 * (j - HB::kNL1) + k);
+  } else if (j < HB::kNL1 + 8) {
+    v = __ldg(w2 + (size_t)(32 * (j - HB::kNL1 - 4) + k) * 128 + r);
+  } else {
+    const int jj = j - HB::kNL1 - 8;
+    const int col = DYN ? (r < 27 ? r : -1) : head_l1_col<DYN>(r, head);
+    if (col >= 0) v = __ldg(w1 + (size_t)(32 * jj + k) * K1 + col);
+  }
   float hi, lo;
   umma::split_tf32(v, hi, lo);
   const uint32_t off = umma::kmajor_off(r, k, N) >> 2;
-  float* blob = wq + hb_woff(j);
+  float* blob = wq + HB::woff(j);
   blob[off] = hi;
   blob[N * rows + off] = lo;
 }
 
-// column permutation of the position/time block (X1T rows 0..79 -> nn.Linear input column 27 + p)
-__global__ void k_head_bwd_colmap(int32_t* __restrict__ map /*[113]*/) {
-  const int r = threadIdx.x;
-  if (r < 80) map[r] = 27 + pos_src_index(r);
-  else if (r < 112) map[r] = (r - 80) < 27 ? (r - 80) : -1;
-  else if (r == 112) map[r] = -2;  // bias
+// X1T row -> nn.Linear input column of layer 1 (-1: padding row, -2: the ones row whose gradient column is d bias)
+template <bool DYN>
+__global__ void k_head_bwd_colmap(int head, int32_t* __restrict__ map) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int kX = HeadBwd<DYN>::kXRows;
+  if (r < kX - 1) map[r] = head_l1_col<DYN>(r, head);
+  else if (r == kX - 1) map[r] = -2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -449,30 +580,47 @@ static inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 extern "C" {
 
-int dynrf_head_bwd_wfloats(void) { return kHbWFloats; }
+int dynrf_head_bwd_wfloats(int dynamic) { return dynamic ? HeadBwd<true>::kWFloats : HeadBwd<false>::kWFloats; }
 int dynrf_head_bwd_cst_floats(void) { return kHbCst; }
+int dynrf_head_bwd_xrows(int dynamic) { return dynamic ? HeadBwd<true>::kXRows : HeadBwd<false>::kXRows; }
 
-int dynrf_pack_head_bwd(const float* w1, const float* w2, float* wq, int32_t* colmap, void* stream) {
+int dynrf_pack_head_bwd(int dynamic, int head, const float* w1, const float* w2, float* wq, int32_t* colmap, void* stream) {
   if (!w1 || !w2 || !wq || !colmap) return DYNRF_E_ARG;
-  k_pack_head_bwd<<<(kHbWFloats / 2 + 255) / 256, 256, 0, S_(stream)>>>(w1, w2, wq);
-  k_head_bwd_colmap<<<1, 128, 0, S_(stream)>>>(colmap);
+  if (dynamic) {
+    if (head != DYNRF_HEAD_FEA_LATE_VIEW) return DYNRF_E_UNSUPPORTED;
+    k_pack_head_bwd<true><<<(HeadBwd<true>::kWFloats / 2 + 255) / 256, 256, 0, S_(stream)>>>(w1, 107, w2, head, wq);
+    k_head_bwd_colmap<true><<<1, 192, 0, S_(stream)>>>(head, colmap);
+  } else {
+    if (head != DYNRF_HEAD_FEA && head != DYNRF_HEAD_FEA_TIMEEMB) return DYNRF_E_UNSUPPORTED;
+    k_pack_head_bwd<false><<<(HeadBwd<false>::kWFloats / 2 + 255) / 256, 256, 0, S_(stream)>>>(w1, head == DYNRF_HEAD_FEA ? 138 : 135, w2,
+                                                                                                head, wq);
+    k_head_bwd_colmap<false><<<1, 192, 0, S_(stream)>>>(head, colmap);
+  }
   DYNRF_CHECK_LAUNCH();
   return 0;
 }
 
-int dynrf_dyn_head_bwd_tc(const dynrf_field_cfg_t* cfg, const float* wq, const float* cst, const float* rays, const float* xyz,
-                          const float* tfeat, const float* featT, const float* grgb, const int32_t* active_idx,
-                          const int32_t* active_count, int N, int S, int ld, float* X1T, float* H1T, float* H2T, float* DH2T,
-                          float* DH1T, float* DOT, float* DFT, float* gw3v, float* gb3, void* stream) {
-  if (!cfg || !wq || !cst || !rays || !xyz || !tfeat || !featT || !grgb || !active_idx || !active_count || !X1T || !H1T || !H2T ||
-      !DH2T || !DH1T || !DOT || !DFT || !gw3v || !gb3 || N <= 0 || S <= 0 || ld < N * S || (ld & 3))
+int dynrf_head_bwd_tc(const dynrf_field_cfg_t* cfg, int dynamic, const float* wq, const float* cst, const float* rays, const float* xyz,
+                      const float* tfeat, const float* featT, const float* grgb, const int32_t* active_idx,
+                      const int32_t* active_count, int N, int S, int ld, float* X1T, float* H1T, float* H2T, float* DH2T,
+                      float* DH1T, float* DOT, float* DFT, float* gw3v, float* gb3, float* gviewdir, void* stream) {
+  if (!cfg || !wq || !cst || !rays || !xyz || (dynamic && !tfeat) || !featT || !grgb || !active_idx || !active_count || !X1T || !H1T ||
+      !H2T || !DH2T || !DH1T || !DOT || !DFT || !gw3v || !gb3 || N <= 0 || S <= 0 || ld < N * S || (ld & 3))
     return DYNRF_E_ARG;
   if ((uintptr_t)wq & 15) return DYNRF_E_ALIGN;
-  cudaError_t e = cudaFuncSetAttribute(k_head_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHbSmem);
-  if (e != cudaSuccess) return (int)e;
-  HeadBwdArgs a{wq, cst, rays, xyz, tfeat, featT, grgb, active_idx, active_count, S, ld, X1T, H1T, H2T, DH2T, DH1T, DOT, DFT, gw3v, gb3};
+  HeadBwdArgs a{wq, cst, rays, xyz, tfeat, featT, grgb, active_idx, active_count, S, ld, X1T, H1T, H2T, DH2T, DH1T, DOT, DFT, gw3v, gb3,
+                dynamic ? nullptr : gviewdir};
   const int grid = min((N * S + kTileM - 1) / kTileM, sm_count());
-  k_head_bwd_tc<<<grid, kTc3Threads, kHbSmem, S_(stream)>>>(*cfg, a);
+  cudaError_t e;
+  if (dynamic) {
+    e = cudaFuncSetAttribute(k_head_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHbSmem);
+    if (e != cudaSuccess) return (int)e;
+    k_head_bwd_tc<true><<<grid, kTc3Threads, kHbSmem, S_(stream)>>>(*cfg, a);
+  } else {
+    e = cudaFuncSetAttribute(k_head_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHbSmem);
+    if (e != cudaSuccess) return (int)e;
+    k_head_bwd_tc<false><<<grid, kTc3Threads, kHbSmem, S_(stream)>>>(*cfg, a);
+  }
   DYNRF_CHECK_LAUNCH();
   return 0;
 }

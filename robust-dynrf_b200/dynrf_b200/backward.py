@@ -124,6 +124,9 @@ class StaticFieldFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, ray_type, rays, xyz, z_vals, valid, *params):
         st = ops.static_forward_raw(model, rays.detach(), xyz.detach(), z_vals.detach(), valid, ray_type)
+        if ops.USE_TC:   # basis outputs, kept for the tensor-core head backward
+            st["ldf"] = ops.round_up(st["sigma"].numel(), 128)
+            st["featT"] = torch.empty(32, st["ldf"], device=st["sigma"].device)
         ops.static_app_raw(model, st, ray_type)
         ctx.model, ctx.ray_type, ctx.st = model, ray_type, st
         ctx.set_materialize_grads(False)
@@ -150,7 +153,10 @@ class StaticFieldFn(torch.autograd.Function):
         gden_p, gden_l, gden = _vm_grads(m.density_plane, m.density_line)
         gapp_p, gapp_l, gapp = _vm_grads(m.app_plane, m.app_line)
         gl = {k: GradLayer(pk[k]) for k in ("basis", "h1", "h2", "h3")}
-        if grgb is not None:
+        tc_head = None
+        if grgb is not None and ops.USE_TC and st.get("featT") is not None:
+            tc_head = _head_bwd_tc(m, cfg, st, st["xyz"], None, _f32c(grgb), gl, gapp, gxyz, gvd, n, s)
+        elif grgb is not None:
             vapp = ops.vm_struct(m.app_plane, m.app_line)
             wb2 = pack_bwd(pk["h2"], 0, 128, 128)
             wb1 = pack_bwd(pk["h1"], 0, pk["h1"].K, 128)
@@ -165,9 +171,12 @@ class StaticFieldFn(torch.autograd.Function):
                                              _p(st["sigma"]), _p(gsig), n, s, _p(gxyz), _stream()), "dynrf_static_density_bwd")
         grays = _rays_grad_from(st["rays"], st["z_vals"], float(m.distance_scale), gd, gvd) if need_rays else None
         gb, _ = gl["basis"].unpack()
-        g1w, g1b = gl["h1"].unpack()
-        g2w, g2b = gl["h2"].unpack()
-        g3w, g3b = gl["h3"].unpack()
+        if tc_head is not None:
+            (g1w, g1b), (g2w, g2b), (g3w, g3b) = tc_head["h1"], tc_head["h2"], tc_head["h3"]
+        else:
+            g1w, g1b = gl["h1"].unpack()
+            g2w, g2b = gl["h2"].unpack()
+            g3w, g3b = gl["h3"].unpack()
         pg = gden_p + gden_l + gapp_p + gapp_l + [gb, g1w, g1b, g2w, g2b, g3w, g3b]
         return (None, None, grays, gxyz, None, None, *pg)
 
@@ -218,7 +227,7 @@ class DynamicFieldFn(torch.autograd.Function):
         gapp_p, gapp_l, gapp = _vm_grads(m.app_plane, m.app_line)
         tc_head = None
         if grgb is not None and ops.USE_TC and r.get("featT") is not None:
-            tc_head = _dyn_head_bwd_tc(m, cfg, r, _f32c(grgb), gl, gapp, gxp, n, s)
+            tc_head = _head_bwd_tc(m, cfg, r, r["xyz_prime"], r["tfeat"], _f32c(grgb), gl, gapp, gxp, None, n, s)
         elif grgb is not None:
             vapp = ops.vm_struct(m.app_plane, m.app_line)
             wb2 = pack_bwd(pk["h2"], 0, 128, 128)
@@ -268,29 +277,31 @@ class DynamicFieldFn(torch.autograd.Function):
 
 
 class _HeadBwdState:
-    """Per-model packed weights / constants / scratch of the tensor-core head backward."""
+    """Per-model packed weights / constants / scratch of the tensor-core head backward (either field)."""
 
     def __init__(self, m):
         lib = L.load()
         dev = m.basis_mat.weight.device
-        self.wq = torch.empty(lib.dynrf_head_bwd_wfloats(), device=dev)
+        self.dyn = 1 if m.is_dynamic else 0
+        self.xrows = lib.dynrf_head_bwd_xrows(self.dyn)
+        self.wq = torch.empty(lib.dynrf_head_bwd_wfloats(self.dyn), device=dev)
         self.cst = torch.empty(lib.dynrf_head_bwd_cst_floats(), device=dev)
-        self.colmap = torch.empty(113, dtype=torch.int32, device=dev)
+        self.colmap = torch.empty(self.xrows, dtype=torch.int32, device=dev)
         self.key = None
         self.src_rows = None
         self.bufs = {}
 
     def refresh(self, m):
-        rm = m.renderModule
-        l1, l2, l3 = rm.mlp[0], rm.mlp[2], rm.mlp_view[0]
+        tbl = m._layer_table()
+        l1, l2, l3 = tbl["h1"], tbl["h2"], tbl["h3"]
         key = (ops.PARAM_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias))
         if key != self.key:
             with torch.no_grad():
-                L.check(L.load().dynrf_pack_head_bwd(_p(_f32c(l1.weight.detach())), _p(_f32c(l2.weight.detach())), _p(self.wq),
-                                                     _p(self.colmap), _stream()), "dynrf_pack_head_bwd")
+                L.check(L.load().dynrf_pack_head_bwd(self.dyn, m.head_mode, _p(_f32c(l1.weight.detach())), _p(_f32c(l2.weight.detach())),
+                                                     _p(self.wq), _p(self.colmap), _stream()), "dynrf_pack_head_bwd")
                 w3 = l3.weight.detach()
-                torch.cat((l1.bias.detach(), l2.bias.detach(), w3[:, :128].t().reshape(-1), w3[:, 128:131].t().reshape(-1),
-                           l3.bias.detach()), out=self.cst)
+                w3v = w3[:, 128:131].t().reshape(-1) if w3.shape[1] == 131 else torch.zeros(9, device=w3.device)
+                torch.cat((l1.bias.detach(), l2.bias.detach(), w3[:, :128].t().reshape(-1), w3v, l3.bias.detach()), out=self.cst)
                 if self.src_rows is None:                                   # constant map, resolved once (host sync)
                     cm = self.colmap.long()
                     self.src_rows = torch.nonzero(cm >= 0).reshape(-1)     # X1T rows that map to a layer-1 input column
@@ -301,7 +312,7 @@ class _HeadBwdState:
     def scratch(self, ld, dev):
         b = self.bufs.get(ld)
         if b is None:
-            b = self.bufs[ld] = dict(X1T=torch.empty(113, ld, device=dev), H1T=torch.empty(128, ld, device=dev),
+            b = self.bufs[ld] = dict(X1T=torch.empty(self.xrows, ld, device=dev), H1T=torch.empty(128, ld, device=dev),
                                      H2T=torch.empty(128, ld, device=dev), DH2T=torch.empty(128, ld, device=dev),
                                      DH1T=torch.empty(128, ld, device=dev), DOT=torch.empty(4, ld, device=dev),
                                      DFT=torch.empty(32, ld, device=dev))
@@ -312,8 +323,9 @@ def _wgrad(XT, K, DYT, N, ld, cnt, out, out_ld):
     L.check(L.load().dynrf_wgrad_gemm(_p(XT), ld, K, _p(DYT), ld, N, ld, _p(cnt), _p(out), out_ld, _stream()), "dynrf_wgrad_gemm")
 
 
-def _dyn_head_bwd_tc(m, cfg, r, grgb, gl, gapp, gxp, n, s):
-    """Tensor-core appearance-head backward: fused tile kernel (recompute + data gradients) -> wgrad GEMMs -> basis / lookups."""
+def _head_bwd_tc(m, cfg, r, coords, tfeat, grgb, gl, gapp, gcoord, gvd, n, s):
+    """Tensor-core appearance-head backward: fused tile kernel (recompute + data gradients) -> wgrad GEMMs -> basis / lookups.
+    r: forward record (rays, xyz, featT, ldf, idx, cnt); coords: lookup coordinates; gcoord: their gradient (+=) or None."""
     lib = L.load()
     st = m.__dict__.get("_head_bwd_state")
     if st is None:
@@ -322,31 +334,37 @@ def _dyn_head_bwd_tc(m, cfg, r, grgb, gl, gapp, gxp, n, s):
     dev = grgb.device
     ld = r["ldf"]
     b = st.scratch(ld, dev)
+    xr = st.xrows
+    l1 = m._layer_table()["h1"]
+    k1 = l1.weight.shape[1]
     gw3v = torch.zeros(3, 3, device=dev)
     gb3 = torch.zeros(3, device=dev)
-    L.check(lib.dynrf_dyn_head_bwd_tc(C.byref(cfg), _p(st.wq), _p(st.cst), _p(r["rays"]), _p(r["xyz"]), _p(r["tfeat"]), _p(r["featT"]),
-                                      _p(grgb), _p(r["idx"]), _p(r["cnt"]), n, s, ld, _p(b["X1T"]), _p(b["H1T"]), _p(b["H2T"]),
-                                      _p(b["DH2T"]), _p(b["DH1T"]), _p(b["DOT"]), _p(b["DFT"]), _p(gw3v), _p(gb3), _stream()),
-            "dynrf_dyn_head_bwd_tc")
+    L.check(lib.dynrf_head_bwd_tc(C.byref(cfg), st.dyn, _p(st.wq), _p(st.cst), _p(r["rays"]), _p(r["xyz"]), _p(tfeat), _p(r["featT"]),
+                                  _p(grgb), _p(r["idx"]), _p(r["cnt"]), n, s, ld, _p(b["X1T"]), _p(b["H1T"]), _p(b["H2T"]),
+                                  _p(b["DH2T"]), _p(b["DH1T"]), _p(b["DOT"]), _p(b["DFT"]), _p(gw3v), _p(gb3), _p(gvd), _stream()),
+            "dynrf_head_bwd_tc")
     cnt = r["cnt"]
-    dw1m = torch.zeros(128, 113, device=dev)
-    _wgrad(b["X1T"], 113, b["DH1T"], 128, ld, cnt, dw1m, 113)
-    dw1 = torch.zeros(128, 107, device=dev)
+    dw1m = torch.zeros(128, xr, device=dev)
+    _wgrad(b["X1T"], xr, b["DH1T"], 128, ld, cnt, dw1m, xr)
+    dw1 = torch.zeros(128, k1, device=dev)
     dw1[:, st.dst_cols] = dw1m[:, st.src_rows]
-    db1 = dw1m[:, 112].contiguous()
+    db1 = dw1m[:, xr - 1].contiguous()
     dw2 = torch.zeros(128, 128, device=dev)
     _wgrad(b["H1T"], 128, b["DH2T"], 128, ld, cnt, dw2, 128)
     db2 = torch.zeros(128, 1, device=dev)
-    _wgrad(b["X1T"][112:113], 1, b["DH2T"], 128, ld, cnt, db2, 1)   # ones row -> column sums
-    dw3 = torch.zeros(3, 131, device=dev)
-    _wgrad(b["H2T"], 128, b["DOT"], 3, ld, cnt, dw3, 131)
-    dw3[:, 128:131] = gw3v
+    _wgrad(b["X1T"][xr - 1:xr], 1, b["DH2T"], 128, ld, cnt, db2, 1)   # ones row -> column sums
+    k3 = m._layer_table()["h3"].weight.shape[1]
+    dw3 = torch.zeros(3, k3, device=dev)
+    _wgrad(b["H2T"], 128, b["DOT"], 3, ld, cnt, dw3, k3)
+    if k3 == 131:
+        dw3[:, 128:131] = gw3v
     # basis_mat + lookups (SIMT tile kernel)
     pk = m._packed
     vapp = ops.vm_struct(m.app_plane, m.app_line)
-    wbB = torch.cat([pack_bwd(pk["basis"], 72 * i, 72 * i + 72, 32) for i in range(3)])
-    L.check(lib.dynrf_basis_bwd(C.byref(cfg), 1, C.byref(vapp), C.byref(gapp), _p(wbB), _p(r["xyz_prime"]), _p(b["DFT"]), ld, n, s,
-                                _p(r["idx"]), _p(cnt), _p(gl["basis"].dwt), _p(gxp), _stream()), "dynrf_basis_bwd")
+    nstr = 3 if st.dyn else 1
+    wbB = torch.cat([pack_bwd(pk["basis"], 72 * i, 72 * i + 72, 32) for i in range(nstr)])
+    L.check(lib.dynrf_basis_bwd(C.byref(cfg), st.dyn, C.byref(vapp), C.byref(gapp), _p(wbB), _p(coords), _p(b["DFT"]), ld, n, s,
+                                _p(r["idx"]), _p(cnt), _p(gl["basis"].dwt), _p(gcoord), _stream()), "dynrf_basis_bwd")
     return {"h1": (dw1, db1), "h2": (dw2, db2.reshape(-1)), "h3": (dw3, gb3)}
 
 

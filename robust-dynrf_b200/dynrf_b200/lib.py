@@ -112,10 +112,11 @@ PROTOTYPES = {
     "dynrf_dyn_mlp_bwd": [_cfg, _I, _vm, _vg, _ly, _ly, _P, _P, _P, _P, _P, _I, _I, _P, _lg, _lg, _P, _P],
     "dynrf_warp_bwd": [_cfg, _P, _I, _I, _P, _ly, _ly, _ly, _P, _P, _P, _lg, _lg, _lg, _P, _P],
     "dynrf_time_embed_bwd": [_P, _I, _ly, _ly, _P, _lg, _lg, _P],
-    "dynrf_head_bwd_wfloats": [],
+    "dynrf_head_bwd_wfloats": [_I],
+    "dynrf_head_bwd_xrows": [_I],
     "dynrf_head_bwd_cst_floats": [],
-    "dynrf_pack_head_bwd": [_P, _P, _P, _P, _P],
-    "dynrf_dyn_head_bwd_tc": [_cfg, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "dynrf_pack_head_bwd": [_I, _I, _P, _P, _P, _P, _P],
+    "dynrf_head_bwd_tc": [_cfg, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "dynrf_app_fwd_wfloats": [_I],
     "dynrf_app_fwd_cst_floats": [],
     "dynrf_pack_app_fwd": [_I, _I, _P, _P, _P, _P, _P],
@@ -136,7 +137,7 @@ PROTOTYPES = {
 }
 
 _lib = None
-_NO_LAUNCH = {"dynrf_abi_version", "dynrf_pad_k", "dynrf_pad_n", "dynrf_strerror", "dynrf_sb_umma_floats", "dynrf_head_bwd_wfloats", "dynrf_head_bwd_cst_floats", "dynrf_sb_bwd_wfloats", "dynrf_app_fwd_wfloats", "dynrf_app_fwd_cst_floats"}
+_NO_LAUNCH = {"dynrf_abi_version", "dynrf_pad_k", "dynrf_pad_n", "dynrf_strerror", "dynrf_sb_umma_floats", "dynrf_head_bwd_wfloats", "dynrf_head_bwd_cst_floats", "dynrf_head_bwd_xrows", "dynrf_sb_bwd_wfloats", "dynrf_app_fwd_wfloats", "dynrf_app_fwd_cst_floats"}
 
 # every other entry point enqueues exactly one kernel of this library; bench.py reports the count
 launch_count = 0
