@@ -271,8 +271,9 @@ int dynrf_dyn_sigma_blend_fwd_tc2(const dynrf_field_cfg_t* cfg, const dynrf_vm_t
  *   ones row whose gradient column is d bias).
  * dynrf_head_bwd_tc: cst = [b1(128) | b2(128) | W3[:, :128]^T (128x3) | W3[:, 128:131]^T (3x3, zeros for DYNRF_HEAD_FEA) | b3(3)];
  *   featT [32][ld] = basis outputs saved by dynrf_app_fwd_tc; writes feature-major [rows][ld] tensors X1T[xrows] H1T[128]
- *   H2T[128] DH2T[128] DH1T[128] DOT[3] DFT[32] (column j = j-th active sample) and accumulates gw3v [3][3] (d W3[:, 128+k]),
- *   gb3 [3] and (static MLP_Fea head, optional) gviewdir [N][3].  ld >= round_up(N*S,128), multiple of 4.
+ *   DH2T[128] DH1T[128] DFT[32] (column j = j-th active sample) for the weight-gradient GEMMs and accumulates gw3h [3][128]
+ *   (d W3[:, :128]), gw3v [3][3] (d W3[:, 128+k]), gb3 [3], gb2 [128] and (static MLP_Fea head, optional) gviewdir [N][3].
+ *   ld >= round_up(N*S,128), multiple of 4.
  * dynrf_basis_bwd: DFT -> packed basis gradient [K][32] (+=), plane / line gradients (+=), d loss / d coords (+=). */
 int dynrf_head_bwd_wfloats(int dynamic);
 int dynrf_head_bwd_cst_floats(void);
@@ -280,8 +281,8 @@ int dynrf_head_bwd_xrows(int dynamic);
 int dynrf_pack_head_bwd(int dynamic, int head, const float* w1, const float* w2, float* wq, int32_t* colmap, void* stream);
 int dynrf_head_bwd_tc(const dynrf_field_cfg_t* cfg, int dynamic, const float* wq, const float* cst, const float* rays, const float* xyz,
                       const float* tfeat, const float* featT, const float* grgb, const int32_t* active_idx,
-                      const int32_t* active_count, int N, int S, int ld, float* X1T, float* H1T, float* H2T, float* DH2T,
-                      float* DH1T, float* DOT, float* DFT, float* gw3v, float* gb3, float* gviewdir, void* stream);
+                      const int32_t* active_count, int N, int S, int ld, float* X1T, float* H1T, float* DH2T, float* DH1T,
+                      float* DFT, float* gw3h, float* gw3v, float* gb3, float* gb2, float* gviewdir, void* stream);
 int dynrf_basis_bwd(const dynrf_field_cfg_t* cfg, int dynamic, const dynrf_vm_t* app, const dynrf_vm_grad_t* gapp, const float* wbB,
                     const float* coords, const float* DFT, int ld, int N, int S, const int32_t* active_idx,
                     const int32_t* active_count, float* gbasis_wt, float* gcoord, void* stream);

@@ -203,6 +203,21 @@ __device__ __forceinline__ TapB tapb(float x, int n, int s) {
   return TapB{t.i0, t.i1, t.r0, t.r1, t.scale, t.v0, t.v1};
 }
 
+// v[c] holds this lane's value of column c; returns (in lane L) the sum over the 32 lanes of column L
+__device__ __forceinline__ float warp_col_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
 constexpr int kProdThreads = 512;
 constexpr int kTc3Threads = kProdThreads + 32;
 

@@ -64,13 +64,13 @@ struct HeadBwdArgs {
   float* X1T;   // dynamic [113]: 80 position/time rows (this kernel's K order) | 32 feat rows | ones
                 // static  [161]: 4 x 32 encoding rows | 27 feat + 3 viewdir + 2 zero rows | ones
   float* H1T;   // [128]
-  float* H2T;   // [128]
   float* DH2T;  // [128]
   float* DH1T;  // [128]
-  float* DOT;   // [3]
   float* DFT;   // [32]
   float* gw3v;  // [3][3] += d W3[:, 128+k]   (row c, col k)
   float* gb3;   // [3]    += d b3
+  float* gw3h;  // [3][128] += d W3[:, :128]
+  float* gb2;   // [128]  += d b2
   float* gvd;   // [N][3] += d loss / d viewdir through layer 1 (static MLP_Fea head, optional)
 };
 
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
     const int em = q * 32 + lane;            // sample row this thread owns in the epilogues
     const AabbNorm nb = make_norm(cfg);
     const int ld = a.ld;
-    float acc_vd[9], acc_b3[3];
+    float acc_vd[9], acc_b3[3], acc_w3[3] = {0.f, 0.f, 0.f}, acc_b2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 9; ++i) acc_vd[i] = 0.f;
 #pragma unroll
@@ -293,9 +293,6 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) part[(cb * 3 + c) * kTileM + em] = po[c];
-#pragma unroll
-        for (int qq = 0; qq < 8; ++qq)
-          store_quad_g(a.H2T, ld, cb * 32 + qq * 4, jg0 + em, make_float4(h2[qq * 4], h2[qq * 4 + 1], h2[qq * 4 + 2], h2[qq * 4 + 3]));
         prod_bar();
         if (tid < kTileM) {
           const bool onm = scr.on[tid] != 0;
@@ -309,7 +306,6 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
             const float rgbv = sigmoidf_(o);
             g3[c] = onm ? __ldg(a.grgb + (size_t)scr.idx[tid] * 3 + c) * rgbv * (1.0f - rgbv) : 0.f;
             go[c * kTileM + tid] = g3[c];
-            a.DOT[(size_t)c * ld + jg0 + tid] = g3[c];
             acc_b3[c] += g3[c];
           }
 #pragma unroll
@@ -319,11 +315,24 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
         }
         prod_bar();
         const float g0 = go[em], g1 = go[kTileM + em], g2 = go[2 * kTileM + em];
+        {
+          // d W3[c][n] += sum_m h2[m][n] g_c[m]: column sums over this warp's 32 samples, kept in registers (lane <-> column)
+          float red[32];
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const int n = cb * 32 + jj;
-          const float d = fmaf(W3t[n * 3 + 0], g0, fmaf(W3t[n * 3 + 1], g1, W3t[n * 3 + 2] * g2));
-          h2[jj] = h2[jj] > 0.f ? d : 0.f;
+          for (int c = 0; c < 3; ++c) {
+            const float gc = c == 0 ? g0 : (c == 1 ? g1 : g2);
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) red[jj] = h2[jj] * gc;
+            acc_w3[c] += warp_col_reduce32(red, lane);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int n = cb * 32 + jj;
+            const float d = fmaf(W3t[n * 3 + 0], g0, fmaf(W3t[n * 3 + 1], g1, W3t[n * 3 + 2] * g2));
+            h2[jj] = h2[jj] > 0.f ? d : 0.f;
+            red[jj] = h2[jj];
+          }
+          acc_b2 += warp_col_reduce32(red, lane);
         }
 #pragma unroll 1
         for (int c4 = 0; c4 < 4; ++c4) {
@@ -416,6 +425,9 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
       umma::fence_before_sync();
       prod_bar();
     }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) atomicAdd(a.gw3h + c * 128 + cb * 32 + lane, acc_w3[c]);
+    atomicAdd(a.gb2 + cb * 32 + lane, acc_b2);
     if (tid < kTileM) {
 #pragma unroll
       for (int i = 0; i < 9; ++i) atomicAdd(a.gw3v + i, warp_sum(acc_vd[i]) * (lane == 0 ? 1.f : 0.f));
@@ -602,13 +614,13 @@ int dynrf_pack_head_bwd(int dynamic, int head, const float* w1, const float* w2,
 
 int dynrf_head_bwd_tc(const dynrf_field_cfg_t* cfg, int dynamic, const float* wq, const float* cst, const float* rays, const float* xyz,
                       const float* tfeat, const float* featT, const float* grgb, const int32_t* active_idx,
-                      const int32_t* active_count, int N, int S, int ld, float* X1T, float* H1T, float* H2T, float* DH2T,
-                      float* DH1T, float* DOT, float* DFT, float* gw3v, float* gb3, float* gviewdir, void* stream) {
+                      const int32_t* active_count, int N, int S, int ld, float* X1T, float* H1T, float* DH2T, float* DH1T,
+                      float* DFT, float* gw3h, float* gw3v, float* gb3, float* gb2, float* gviewdir, void* stream) {
   if (!cfg || !wq || !cst || !rays || !xyz || (dynamic && !tfeat) || !featT || !grgb || !active_idx || !active_count || !X1T || !H1T ||
-      !H2T || !DH2T || !DH1T || !DOT || !DFT || !gw3v || !gb3 || N <= 0 || S <= 0 || ld < N * S || (ld & 3))
+      !DH2T || !DH1T || !DFT || !gw3h || !gw3v || !gb3 || !gb2 || N <= 0 || S <= 0 || ld < N * S || (ld & 3))
     return DYNRF_E_ARG;
   if ((uintptr_t)wq & 15) return DYNRF_E_ALIGN;
-  HeadBwdArgs a{wq, cst, rays, xyz, tfeat, featT, grgb, active_idx, active_count, S, ld, X1T, H1T, H2T, DH2T, DH1T, DOT, DFT, gw3v, gb3,
+  HeadBwdArgs a{wq, cst, rays, xyz, tfeat, featT, grgb, active_idx, active_count, S, ld, X1T, H1T, DH2T, DH1T, DFT, gw3v, gb3, gw3h, gb2,
                 dynamic ? nullptr : gviewdir};
   const int grid = min((N * S + kTileM - 1) / kTileM, sm_count());
   cudaError_t e;

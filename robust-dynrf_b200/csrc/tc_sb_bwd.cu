@@ -70,21 +70,6 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float4& r) {
   r = make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
 }
 
-// v[c] holds this lane's value of column c; returns (in lane L) the sum over the 32 lanes of column L
-__device__ __forceinline__ float warp_col_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float send = up ? v[i] : v[i + s];
-      const float keep = up ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
-
 constexpr size_t kSbbSmem = (size_t)(3 * kOpFloats + 2 * kWSlotFloats + kSbbCst + 4 * kTileM + 2 * kTileM) * sizeof(float) +
                             sizeof(TapsSmemB) + sizeof(TileScratch<kTileM>) + 128;
 

@@ -313,8 +313,7 @@ class _HeadBwdState:
         b = self.bufs.get(ld)
         if b is None:
             b = self.bufs[ld] = dict(X1T=torch.empty(self.xrows, ld, device=dev), H1T=torch.empty(128, ld, device=dev),
-                                     H2T=torch.empty(128, ld, device=dev), DH2T=torch.empty(128, ld, device=dev),
-                                     DH1T=torch.empty(128, ld, device=dev), DOT=torch.empty(4, ld, device=dev),
+                                     DH2T=torch.empty(128, ld, device=dev), DH1T=torch.empty(128, ld, device=dev),
                                      DFT=torch.empty(32, ld, device=dev))
         return b
 
@@ -337,11 +336,11 @@ def _head_bwd_tc(m, cfg, r, coords, tfeat, grgb, gl, gapp, gcoord, gvd, n, s):
     xr = st.xrows
     l1 = m._layer_table()["h1"]
     k1 = l1.weight.shape[1]
-    gw3v = torch.zeros(3, 3, device=dev)
-    gb3 = torch.zeros(3, device=dev)
+    small = torch.zeros(3 * 128 + 9 + 3 + 128, device=dev)    # gw3h [3][128] | gw3v [3][3] | gb3 [3] | gb2 [128]
+    gw3h, gw3v, gb3, gb2 = small[:384].view(3, 128), small[384:393].view(3, 3), small[393:396], small[396:524]
     L.check(lib.dynrf_head_bwd_tc(C.byref(cfg), st.dyn, _p(st.wq), _p(st.cst), _p(r["rays"]), _p(r["xyz"]), _p(tfeat), _p(r["featT"]),
-                                  _p(grgb), _p(r["idx"]), _p(r["cnt"]), n, s, ld, _p(b["X1T"]), _p(b["H1T"]), _p(b["H2T"]),
-                                  _p(b["DH2T"]), _p(b["DH1T"]), _p(b["DOT"]), _p(b["DFT"]), _p(gw3v), _p(gb3), _p(gvd), _stream()),
+                                  _p(grgb), _p(r["idx"]), _p(r["cnt"]), n, s, ld, _p(b["X1T"]), _p(b["H1T"]), _p(b["DH2T"]),
+                                  _p(b["DH1T"]), _p(b["DFT"]), _p(gw3h), _p(gw3v), _p(gb3), _p(gb2), _p(gvd), _stream()),
             "dynrf_head_bwd_tc")
     cnt = r["cnt"]
     dw1m = torch.zeros(128, xr, device=dev)
@@ -351,13 +350,8 @@ def _head_bwd_tc(m, cfg, r, coords, tfeat, grgb, gl, gapp, gcoord, gvd, n, s):
     db1 = dw1m[:, xr - 1].contiguous()
     dw2 = torch.zeros(128, 128, device=dev)
     _wgrad(b["H1T"], 128, b["DH2T"], 128, ld, cnt, dw2, 128)
-    db2 = torch.zeros(128, 1, device=dev)
-    _wgrad(b["X1T"][xr - 1:xr], 1, b["DH2T"], 128, ld, cnt, db2, 1)   # ones row -> column sums
     k3 = m._layer_table()["h3"].weight.shape[1]
-    dw3 = torch.zeros(3, k3, device=dev)
-    _wgrad(b["H2T"], 128, b["DOT"], 3, ld, cnt, dw3, k3)
-    if k3 == 131:
-        dw3[:, 128:131] = gw3v
+    dw3 = torch.cat((gw3h, gw3v), 1) if k3 == 131 else gw3h
     # basis_mat + lookups (SIMT tile kernel)
     pk = m._packed
     vapp = ops.vm_struct(m.app_plane, m.app_line)
@@ -365,7 +359,7 @@ def _head_bwd_tc(m, cfg, r, coords, tfeat, grgb, gl, gapp, gcoord, gvd, n, s):
     wbB = torch.cat([pack_bwd(pk["basis"], 72 * i, 72 * i + 72, 32) for i in range(nstr)])
     L.check(lib.dynrf_basis_bwd(C.byref(cfg), st.dyn, C.byref(vapp), C.byref(gapp), _p(wbB), _p(coords), _p(b["DFT"]), ld, n, s,
                                 _p(r["idx"]), _p(cnt), _p(gl["basis"].dwt), _p(gcoord), _stream()), "dynrf_basis_bwd")
-    return {"h1": (dw1, db1), "h2": (dw2, db2.reshape(-1)), "h3": (dw3, gb3)}
+    return {"h1": (dw1, db1), "h2": (dw2, gb2), "h3": (dw3, gb3)}
 
 
 class _SbBwdState:
