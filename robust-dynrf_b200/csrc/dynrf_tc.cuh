@@ -140,7 +140,7 @@ struct Ring {
 
 __device__ __forceinline__ void ring_wait_free(const Ring& r) {
   const uint32_t b = r.chunk % 3, u = r.chunk / 3;
-  if (u > 0) umma::mbar_wait(&r.bar_free[b], (u - 1) & 1);
+  if (u > 0) umma::mbar_wait_backoff(&r.bar_free[b], (u - 1) & 1);
 }
 __device__ __forceinline__ float* ring_abuf(const Ring& r) { return r.abuf + (size_t)(r.chunk % 3) * kOpFloats; }
 

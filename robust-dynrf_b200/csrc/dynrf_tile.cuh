@@ -62,7 +62,8 @@ __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.
 // normalised-coordinate units.  Out-of-range taps carry value 0 (zeros padding) and get no gradient.
 __device__ __forceinline__ float3 vm_group_bwd(const float* __restrict__ plane, const float* __restrict__ line,
                                                float* __restrict__ gplane, float* __restrict__ gline, int C, int W,
-                                               const Tap1& tu, const Tap1& tv, const Tap1& tl, int c, float4 g) {
+                                               const Tap1& tu, const Tap1& tv, const Tap1& tl, int c, float4 g,
+                                               float4* feat = nullptr /* optional: the forward value plane*line of the group */) {
   const size_t o00 = ((size_t)tv.i0 * W + tu.i0) * C + c, o01 = ((size_t)tv.i0 * W + tu.i1) * C + c;
   const size_t o10 = ((size_t)tv.i1 * W + tu.i0) * C + c, o11 = ((size_t)tv.i1 * W + tu.i1) * C + c;
   const bool b00 = tu.v0 && tv.v0, b01 = tu.v1 && tv.v0, b10 = tu.v0 && tv.v1, b11 = tu.v1 && tv.v1;
@@ -78,6 +79,7 @@ __device__ __forceinline__ float3 vm_group_bwd(const float* __restrict__ plane, 
   float4 l = mul4(L0, tl.r0);
   l = fma4(L1, tl.r1, l);
   const float4 dp = mul44(g, l), dl = mul44(g, p);
+  if (feat) *feat = mul44(p, l);
   if (b00) red_add4(gplane + o00, dp.x * w00, dp.y * w00, dp.z * w00, dp.w * w00);
   if (b01) red_add4(gplane + o01, dp.x * w01, dp.y * w01, dp.z * w01, dp.w * w01);
   if (b10) red_add4(gplane + o10, dp.x * w10, dp.y * w10, dp.z * w10, dp.w * w10);
@@ -201,7 +203,8 @@ __device__ __forceinline__ float3 vm_group_bwd_w(const float* __restrict__ plane
 template <int TM, int LD>
 __device__ __forceinline__ void scatter_vm_rows(const dynrf_vm_t& vm, const dynrf_vm_grad_t& gvm, const float (*xq)[TM],
                                                 int stride, int row_base, const float* __restrict__ dA, int tid,
-                                                const int* __restrict__ on, float (*gxs)[TM]) {
+                                                const int* __restrict__ on, float (*gxs)[TM],
+                                                float* __restrict__ Afeat = nullptr /* optional: forward rows (gather_vm_rows) */) {
   constexpr int NPART = kMlpThreads / TM;
   static_assert(TM % 32 == 0, "a warp must hold 32 consecutive samples");
   const int m = tid % TM, part = tid / TM;
@@ -220,8 +223,19 @@ __device__ __forceinline__ void scatter_vm_rows(const dynrf_vm_t& vm, const dynr
     for (int g = (part - q % NPART + NPART) % NPART; g < ng; g += NPART) {
       const float* a = dA + (size_t)(row_base + coff + g * 4) * LD + m;
       const float4 gg = make_float4(a[0], a[LD], a[2 * LD], a[3 * LD]);
-      const float3 r = vm_group_bwd_w(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], C, vm.W[pl], tu, tv, tl, g * 4, gg, act,
-                                        tid & 31);
+      float3 r;
+      if (Afeat) {   // fused recompute: the taps are loaded once for the scatter and for the forward value
+        float4 fv = make_float4(0.f, 0.f, 0.f, 0.f);
+        r = act ? vm_group_bwd(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], C, vm.W[pl], tu, tv, tl, g * 4, gg, &fv)
+                : make_float3(0.f, 0.f, 0.f);
+        float* fa = Afeat + (size_t)(row_base + coff + g * 4) * LD + m;
+        fa[0] = fv.x;
+        fa[LD] = fv.y;
+        fa[2 * LD] = fv.z;
+        fa[3 * LD] = fv.w;
+      } else {
+        r = vm_group_bwd_w(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], C, vm.W[pl], tu, tv, tl, g * 4, gg, act, tid & 31);
+      }
       gacc[u] += r.x;
       gacc[v] += r.y;
       gacc[l] += r.z;

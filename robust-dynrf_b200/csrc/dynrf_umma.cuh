@@ -99,6 +99,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// producer-side wait: polls with a short sleep between attempts so that 16 spinning warps do not take issue slots
+// from the tensor-core warp and from the warps that still have work
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  while (!done) {
+    __nanosleep(40);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns starting at taddr (lane field = warp's lane base)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
   uint32_t u[32];

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
     const int ld = a.ld;
 
     auto wait_chunk = [&](uint32_t c) {
-      umma::mbar_wait(&bar_free[c % 3], (c / 3) & 1);
+      umma::mbar_wait_backoff(&bar_free[c % 3], (c / 3) & 1);
       umma::fence_after_sync();
     };
     auto arrive = [&]() {

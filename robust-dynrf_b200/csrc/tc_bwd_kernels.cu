@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
     for (int i = 0; i < 3; ++i) acc_b3[i] = 0.f;
 
     auto wait_chunk = [&](uint32_t c) {
-      umma::mbar_wait(&bar_free[c % 3], (c / 3) & 1);
+      umma::mbar_wait_backoff(&bar_free[c % 3], (c / 3) & 1);
       umma::fence_after_sync();
     };
     auto arrive = [&]() {
@@ -558,7 +558,14 @@ k_basis_bwd(dynrf_field_cfg_t cfg, dynrf_vm_t vm, dynrf_vm_grad_t gvm, const flo
     __syncthreads();
 #pragma unroll 1
     for (int si = 0; si < NSTR; ++si) {
-      gather_vm_rows<kBT2, kBL2>(vm, scr.xq, 1 << si, 0, Ac, tid, scr.on);
+      {
+        Acc<80, kBT2> acc;
+        acc_init<80, kBT2>(acc, nullptr, tid >> 4);
+        acc_gemm<80, kBT2, kBL2>(acc, dF, 32, wbB + (size_t)si * 32 * 80, wbuf, tid);
+        acc_store<80, kBT2, kBL2, false>(acc, dAc, 72, tid);
+      }
+      // one pass over the taps: scatter d(plane*line) and recompute the forward features for the basis weight gradient
+      scatter_vm_rows<kBT2, kBL2>(vm, gvm, scr.xq, 1 << si, 0, dAc, tid, scr.on, scr.gx, Ac);
       __syncthreads();
       {
         float accB[5][2];
@@ -566,13 +573,6 @@ k_basis_bwd(dynrf_field_cfg_t cfg, dynrf_vm_t vm, dynrf_vm_grad_t gvm, const flo
         wgrad_acc<5, 2, kBT2, kBL2>(accB, Ac, 72, dF, tid);
         wgrad_flush(accB, gbasis_wt + (size_t)si * 72 * 32, 72, 32, tid);
       }
-      {
-        Acc<80, kBT2> acc;
-        acc_init<80, kBT2>(acc, nullptr, tid >> 4);
-        acc_gemm<80, kBT2, kBL2>(acc, dF, 32, wbB + (size_t)si * 32 * 80, wbuf, tid);
-        acc_store<80, kBT2, kBL2, false>(acc, dAc, 72, tid);
-      }
-      scatter_vm_rows<kBT2, kBL2>(vm, gvm, scr.xq, 1 << si, 0, dAc, tid, scr.on, scr.gx);
       __syncthreads();
     }
     if (gcoord && tid < kBT2 && scr.on[tid]) {

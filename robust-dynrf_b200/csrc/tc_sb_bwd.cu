@@ -135,7 +135,7 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
     float accW2 = 0.f, accB1 = 0.f, accB2 = 0.f;
 
     auto wait_chunk = [&](uint32_t c) {
-      umma::mbar_wait(&bar_free[c % 3], (c / 3) & 1);
+      umma::mbar_wait_backoff(&bar_free[c % 3], (c / 3) & 1);
       umma::fence_after_sync();
     };
     auto arrive = [&]() {
