@@ -43,9 +43,12 @@ def _worker(rank, world, port, n_total, tmp):
     params = [torch.nn.Parameter(v.detach().clone()) for v in sd.values()]
     for p, v in zip(params, sd.values()):
         p.grad = None if v.grad is None else v.grad.clone()
+    # the step driver's variant: one flat buffer that every gradient aliases
+    flat = torch.cat([(torch.zeros_like(v) if v.grad is None else v.grad).reshape(-1) for v in sd.values()])
+    P.allreduce_flat_mean(flat, world)
     P.allreduce_mean_grads(params, world)
     if rank == 0:
-        torch.save({"full": full, "grads": {k: p.grad for k, p in zip(sd.keys(), params)}}, tmp)
+        torch.save({"full": full, "grads": {k: p.grad for k, p in zip(sd.keys(), params)}, "flat": flat}, tmp)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -60,6 +63,9 @@ def test_two_rank_sharding_matches_single(tmp_path, n_total):
     sd = {k: v.clone().requires_grad_(True) for k, v in case["sd_dynamic"].items()}
     ref = H.oracle_pass(case)
     torch.testing.assert_close(got["full"], _per_ray(ref["out"]), rtol=1e-5, atol=1e-6)
+    # flat-buffer all-reduce == per-tensor all-reduce
+    flat_ref = torch.cat([(torch.zeros_like(case["sd_dynamic"][k]) if g is None else g).reshape(-1) for k, g in got["grads"].items()])
+    torch.testing.assert_close(got["flat"], flat_ref, rtol=0, atol=0)
     if n_total % world == 0:  # equal shards: mean of per-shard mean-loss gradients == full-batch gradient
         xyz, z, valid = O.sampleXYZ(case["cd"], case["rays"], 24, "ndc", False)
         fs = O.field_forward(case["cs"], case["sd_static"], case["rays"], case["ts"], xyz, z, valid, "ndc")
