@@ -39,6 +39,7 @@ N_SAMPLES = 256
 WORKLOAD = "cfg2: Nvidia.txt Balloon1 shape, static+dynamic VM fields grid [331,368,220], 4096 NDC rays x 256 samples per GPU"
 METRIC = "rays/sec (train step)"
 BYTES_PER_SAMPLE_K1 = 588  # 576 B gathered + 12 B written, samples generated in-kernel
+BYTES_PER_SAMPLE_SBB = 3 * 3456 + 1412 + 57  # k_dyn_mlp_bwd_tc, see DESIGN.md 6
 
 
 def peaks():
@@ -274,6 +275,21 @@ def main():
     ksb = [a.elapsed_time(b) for a, b in (L.profile_events[DOM] or L.profile_events["dynrf_dyn_sigma_blend_fwd"])]
     L.profile_events = None
 
+    # dominant kernel of the train step (largest share in profiles/r01_launch_shares_train.json): eager train steps on a
+    # throw-away Step (it re-points p.grad, so it runs after every timed loop)
+    kdom = []
+    if mode == "train":
+        DOMB = "dynrf_dyn_mlp_bwd_tc"
+        prof2 = TS.Step(static, dyn, N_SAMPLES, "ndc", "train", 1, graph=False)
+        prof2(rays_d, ts_d, target_d)
+        L.profile_events = {DOMB: []}
+        for i in range(5):
+            flush.fill_(i & 0xFF)
+            prof2(rays_d, ts_d, target_d)
+        torch.cuda.synchronize()
+        kdom = [a.elapsed_time(b) for a, b in L.profile_events[DOMB]]
+        L.profile_events = None
+
     tt = torch.tensor([t_ms, t2_ms], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -311,6 +327,16 @@ def main():
                                   "frac": (sb_flops / (ksb_ms * 1e-3) / 1e12 / pk["tf_sust"]) if ksb else None,
                                   "ms_per_launch": ksb_ms, "peak_source": pk["src"],
                                   "note": "useful fp32-equivalent flops (the tensor cores execute 3x this as TF32 passes); bf16 dense peak quoted as the denominator the task names"},
+            "roofline_dominant": None if not kdom else {
+                "kernel": "k_dyn_mlp_bwd_tc (backward of a16+a17: recompute + dgrad on tcgen05, scatter from TMEM, operand streams for the wgrad GEMM)",
+                "bound": "hbm", "achieved": N_RAYS * N_SAMPLES * BYTES_PER_SAMPLE_SBB / (sum(kdom) / len(kdom) * 1e-3) / 1e9,
+                "peak": pk["hbm"], "unit": "GB/s",
+                "frac": N_RAYS * N_SAMPLES * BYTES_PER_SAMPLE_SBB / (sum(kdom) / len(kdom) * 1e-3) / 1e9 / pk["hbm"],
+                "traffic": 1.80e9, "ms_per_launch": sum(kdom) / len(kdom), "bytes_per_sample": BYTES_PER_SAMPLE_SBB,
+                "peak_source": pk["src"],
+                "note": "algorithmic bytes: 3456 gathered + 3456 re-read by the scatter + 3456 reduced + 1412 streamed (X^T 225 rows, dH^T 128 rows) + 57 per-sample I/O; "
+                        "the 21 MB of tables are L2-resident, DRAM traffic (ncu, profiles/r01_ncu_full_bwd_summary.json) is 1.8 GB/launch, almost all of it the operand streams; "
+                        "the kernel is bound by producer-side instruction issue, not by HBM"},
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": int(rays_pin.numel() * 4 + ts_pin.numel() * 4 + target_pin.numel() * 4),
                     "d2h_bytes_per_step": int(out_pin.numel() * 4), "ms_per_step": t2_ms / args.steps},
             "gpu_launches": launches, "clocks": clocks,

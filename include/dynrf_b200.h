@@ -330,10 +330,6 @@ int dynrf_wgrad_gemm(const float* XT, int ldx, int K, const float* DYT, int ldy,
 /* Self-test of the tcgen05 tile-GEMM building block: C[128][N] = A[128][K] x B[N][K]^T, N in {32,64,128},
  * passes = 1 (TF32) or 3 (split TF32, ~fp32 accuracy).  Used by tests/test_gpu_umma.py. */
 int dynrf_selftest_umma_gemm(const float* A, const float* B, int K, int N, int passes, float* C, void* stream);
-/* transposed product on forward-style operands (the weight-gradient form): C[128][64] (rows k < K valid) =
- * A[128][K]^T x B[128][64], operands read MN-major; passes 1 (hi*hi) or 2 (+ hi*lo). */
-int dynrf_selftest_umma_wgrad(const float* A, const float* B, int K, int passes, float* C, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

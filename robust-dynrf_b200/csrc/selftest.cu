@@ -97,100 +97,9 @@ __global__ void __launch_bounds__(256) k_selftest_umma(const float* __restrict__
   if (warp == 0) umma::tmem_dealloc(tmem, N < 32 ? 32 : N);
 }
 
-// Transposed ("weight-gradient") product on the same operand buffers: C[k][n] = sum_m A[m][k] * B[m][n].
-// A and B are staged exactly like forward operands (rows = samples m, K-major in k / n); the MMA reads them as
-// MN-major operands (a_major = b_major = 1): MN blocks of 4 at SBO = R*16 bytes, 8-sample blocks at LBO = 128 bytes.
-// K (features of A) must be <= 128 (zero padded to 128 = UMMA M), N in {64}; passes: 1 = hi*hi, 2 = hi*hi + hi*lo.
-__global__ void __launch_bounds__(256) k_selftest_umma_wgrad(const float* __restrict__ A, const float* __restrict__ B, int K, int passes,
-                                                             float* __restrict__ C, int lbo, int sbo) {
-  constexpr int N = 64;
-  extern __shared__ __align__(128) uint8_t smem[];
-  float* a_hi = reinterpret_cast<float*>(smem);  // [128 k][128 m] as K-major operand with R = 128
-  float* b_hi = a_hi + 128 * 128;                // [64 n][128 m]
-  float* b_lo = b_hi + N * 128;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(b_lo + N * 128);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    umma::mbar_init(bar, 1);
-    umma::fence_mbar_init();
-  }
-  if (warp == 0) umma::tmem_alloc(tslot, 64);
-  umma::fence_before_sync();
-  __syncthreads();
-  umma::fence_after_sync();
-  const uint32_t tmem = *tslot;
-  for (int item = tid; item < 128 * 32; item += 256) {
-    const int m = item % 128, kq = item / 128;
-    float hi[4], lo[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = kq * 4 + j;
-      umma::split_tf32(k < K ? A[(size_t)m * K + k] : 0.f, hi[j], lo[j]);
-    }
-    *reinterpret_cast<float4*>(a_hi + (umma::kmajor_off(m, kq * 4, 128) >> 2)) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-  }
-  for (int item = tid; item < 128 * (N / 4); item += 256) {
-    const int m = item % 128, nq = item / 128;
-    float hi[4], lo[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) umma::split_tf32(B[(size_t)m * N + nq * 4 + j], hi[j], lo[j]);
-    const uint32_t off = umma::kmajor_off(m, nq * 4, 128) >> 2;
-    *reinterpret_cast<float4*>(b_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<float4*>(b_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-  }
-  umma::fence_async_smem();
-  __syncthreads();
-  if (tid == 0) {
-    umma::fence_after_sync();
-    uint32_t idesc = umma::make_idesc_tf32(128, N);
-    if (!(passes & 0x100) || (passes & 0x300) == 0x100) {}
-    const int dbg = passes >> 8; passes &= 0xff;
-    if (dbg == 0) idesc |= (1u << 15) | (1u << 16);  // A and B MN-major
-    else if (dbg == 1) idesc |= (1u << 15);
-    else if (dbg == 2) idesc |= (1u << 16);
-    const uint32_t sa = umma::smem_u32(a_hi);
-    for (int p = 0; p < passes; ++p) {
-      const uint32_t sb = umma::smem_u32(p == 0 ? b_hi : b_lo);
-      for (int ks = 0; ks < 16; ++ks) {  // 8 samples per MMA
-        const uint64_t da = umma::make_desc(sa + ks * 128, lbo, sbo);
-        const uint64_t db = umma::make_desc(sb + ks * 128, lbo, sbo);
-        umma::mma_tf32(tmem, da, db, idesc, (p > 0 || ks > 0) ? 1u : 0u);
-      }
-    }
-    umma::commit(bar);
-  }
-  umma::mbar_wait(bar, 0);
-  umma::fence_after_sync();
-  const int lane_base = 32 * (warp & 3);
-  {
-    const int cb = warp >> 2;
-    float r[32];
-    umma::tmem_ld32(tmem + ((uint32_t)lane_base << 16) + cb * 32, r);
-    const int row = lane_base + lane;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) C[(size_t)row * N + cb * 32 + j] = r[j];
-  }
-  umma::fence_before_sync();
-  __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem, 64);
-}
-
 }  // namespace dynrf
 
 using namespace dynrf;
-
-extern "C" int dynrf_selftest_umma_wgrad_dbg(const float* A, const float* B, int K, int passes, float* C, int lbo, int sbo, void* stream) {
-  if (!A || !B || !C || K <= 0 || K > 128 || (passes & 0xff) < 1 || (passes & 0xff) > 2) return DYNRF_E_ARG;
-  const size_t sm = (size_t)(128 * 128 + 2 * 64 * 128) * 4 + 64;
-  cudaFuncSetAttribute(k_selftest_umma_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  k_selftest_umma_wgrad<<<1, 256, sm, reinterpret_cast<cudaStream_t>(stream)>>>(A, B, K, passes, C, lbo, sbo);
-  DYNRF_CHECK_LAUNCH();
-  return 0;
-}
-extern "C" int dynrf_selftest_umma_wgrad(const float* A, const float* B, int K, int passes, float* C, void* stream) {
-  return dynrf_selftest_umma_wgrad_dbg(A, B, K, passes, C, 128, 2048, stream);
-}
 
 extern "C" int dynrf_selftest_umma_gemm(const float* A, const float* B, int K, int N, int passes, float* C, void* stream) {
   if (!A || !B || !C || K <= 0 || (passes != 1 && passes != 3)) return DYNRF_E_ARG;

@@ -127,7 +127,6 @@ PROTOTYPES = {
     "dynrf_basis_bwd": [_cfg, _I, _vm, _vg, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "dynrf_wgrad_gemm": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _I, _P],
     "dynrf_selftest_umma_gemm": [_P, _P, _I, _I, _I, _P, _P],
-    "dynrf_selftest_umma_wgrad": [_P, _P, _I, _I, _P, _P],
     "dynrf_pack_linear_umma": [_P, _P, _I, _I, _P, _P, _P],
     "dynrf_sb_umma_floats": [],
     "dynrf_pack_sb_umma": [_P, _P, _P, _P],
