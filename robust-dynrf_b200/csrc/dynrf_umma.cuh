@@ -27,9 +27,10 @@ __device__ __forceinline__ uint32_t kmajor_off(int row, int k, int R) {
 
 // hi / lo split of an fp32 value into two tf32-representable parts
 __device__ __forceinline__ float rn_tf32(float a) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a));  // round to nearest, low 13 mantissa bits cleared
-  return __uint_as_float(u);
+  // == cvt.rna.tf32.f32 for finite inputs (round to nearest, ties away from zero; low 13 mantissa bits cleared).  ptxas
+  // expands the cvt into IADD + LOP3 + an inf/nan guard (FSETP + SEL); activations and weights here are finite, and the
+  // guard doubles the cost of the split, which is ~7 % of the instructions of the tile kernels and most of k_wgrad_tc's.
+  return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
   hi = rn_tf32(a);        // |a - hi| <= 2^-11 |a|

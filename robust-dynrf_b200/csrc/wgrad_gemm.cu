@@ -2,8 +2,8 @@
 //
 // XT [K][ldx] and DYT [N][ldy] are feature-major fp32 activations / output-gradients that the fused backward
 // tile kernels stream to global memory (sample index contiguous).  The reduction runs over samples, so both
-// operands are K-major UMMA operands with "K" = samples: rows = features.  Each CTA walks sample chunks of 32,
-// stages the chunk as split-TF32 (hi, lo) operands in shared memory (double buffered), issues 3-pass
+// operands are K-major UMMA operands with "K" = samples: rows = features.  Each CTA walks sample chunks of 64,
+// stages the chunk as split-TF32 (hi, lo) operands in shared memory (one stage, register prefetch of the next), issues 3-pass
 // tcgen05.mma (hi*hi + hi*lo + lo*hi) into a TMEM accumulator that lives for the whole kernel, and finally
 // adds its partial dW into the nn.Linear-layout gradient dw[n * dw_ld + k] with atomics.
 #include "dynrf_common.cuh"
@@ -12,19 +12,21 @@
 namespace dynrf {
 
 constexpr int kWgS = 32;          // samples per chunk (4 MMA k-steps)
+constexpr int kWgQ = kWgS / 4;    // sample quads per chunk
 constexpr int kWgThreads = 256;
 
-// per-thread prefetch registers for one chunk: rows [0, ROWS) x 32 samples, ITEMS = ROWS*8/256 float4 each
+// per-thread prefetch registers for one chunk: rows [0, ROWS) x 64 samples, ITEMS = ROWS*16/256 float4 each
 template <int ROWS>
 struct Pref {
-  static constexpr int ITEMS = (ROWS * (kWgS / 4) + kWgThreads - 1) / kWgThreads;
+  static constexpr int ITEMS = (ROWS * kWgQ + kWgThreads - 1) / kWgThreads;
   float4 v[ITEMS];
 };
 
-// item -> (row, sample quad): lanes r8 fastest (8 rows x 16 B contiguous in the operand), then 8 quads, then row octets
+// item -> (row, sample quad): lanes r8 fastest (8 rows x 16 B contiguous in the operand), then the quads, then row octets.
+// A warp touches 8 rows x 64 contiguous bytes of global memory (full sectors) and 4 x 128 contiguous bytes of shared memory.
 __device__ __forceinline__ void item_rc(int item, int& row, int& sq) {
-  sq = (item >> 3) & 7;
-  row = (item >> 6) * 8 + (item & 7);
+  sq = (item >> 3) & (kWgQ - 1);
+  row = (item / (8 * kWgQ)) * 8 + (item & 7);
 }
 
 template <int ROWS>
@@ -36,7 +38,7 @@ __device__ __forceinline__ void prefetch_rows(Pref<ROWS>& pf, const float* __res
     item_rc(item, row, sq);
     const int p = p0 + sq * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (item < ROWS * (kWgS / 4) && row < nrows && p < P) {
+    if (item < ROWS * kWgQ && row < nrows && p < P) {
       const float* s = src + (size_t)row * ld + p;
       if (p + 3 < P) v = __ldg(reinterpret_cast<const float4*>(s));
       else {
@@ -55,7 +57,7 @@ __device__ __forceinline__ void store_rows(const Pref<ROWS>& pf, float* __restri
 #pragma unroll
   for (int i = 0; i < Pref<ROWS>::ITEMS; ++i) {
     const int item = tid + i * kWgThreads;
-    if (item < ROWS * (kWgS / 4)) {
+    if (item < ROWS * kWgQ) {
       int row, sq;
       item_rc(item, row, sq);
       const float4 v = pf.v[i];
@@ -72,22 +74,23 @@ __device__ __forceinline__ void store_rows(const Pref<ROWS>& pf, float* __restri
   }
 }
 
-// NB = number of 128-row blocks of XT (1 or 2), N = padded output columns (16..128, multiple of 16)
+// NB = number of 128-row blocks of XT (1 or 2), N = padded output columns (16..128, multiple of 16).
+// One shared-memory stage (<= 96 KB) + register prefetch, two CTAs per SM: the global loads of chunk c+1 are in flight while
+// the tensor core consumes chunk c, and one CTA converts / issues while the other CTA's loads land.
 template <int NB, int N>
-__global__ void __launch_bounds__(kWgThreads, 1)
+__global__ void __launch_bounds__(kWgThreads, 2)
 k_wgrad_tc(const float* __restrict__ XT, int ldx, int K, const float* __restrict__ DYT, int ldy, int Nvalid, int Pmax,
            const int32_t* __restrict__ count_ptr, float* __restrict__ dw, int dw_ld) {
   constexpr int kAFloats = 128 * kWgS;  // one 128-row block, hi or lo
   constexpr int kBFloats = N * kWgS;
   constexpr int kStageFloats = 2 * NB * kAFloats + 2 * kBFloats;
   extern __shared__ __align__(128) float smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageFloats);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kStageFloats);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t kCols = NB * N < 32 ? 32 : (NB * N <= 64 ? 64 : (NB * N <= 128 ? 128 : 256));
   if (tid == 0) {
-    umma::mbar_init(&bars[0], 1);
-    umma::mbar_init(&bars[1], 1);
+    umma::mbar_init(bar, 1);
     umma::fence_mbar_init();
   }
   if (warp == 0) umma::tmem_alloc(tslot, kCols);
@@ -98,6 +101,10 @@ k_wgrad_tc(const float* __restrict__ XT, int ldx, int K, const float* __restrict
   const int P = count_ptr ? min(*count_ptr, Pmax) : Pmax;
   const int nchunks = (P + kWgS - 1) / kWgS;
   const uint32_t idesc = umma::make_idesc_tf32(128, N);
+  float* a_hi = smem;
+  float* a_lo = smem + NB * kAFloats;
+  float* b_hi = smem + 2 * NB * kAFloats;
+  float* b_lo = b_hi + kBFloats;
   uint32_t it = 0;
   Pref<NB * 128> pa;
   Pref<N> pb;
@@ -106,20 +113,9 @@ k_wgrad_tc(const float* __restrict__ XT, int ldx, int K, const float* __restrict
     prefetch_rows<N>(pb, DYT, ldy, Nvalid, blockIdx.x * kWgS, P, tid);
   }
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
-    const uint32_t st = it & 1, use = it >> 1;
-    if (use > 0) umma::mbar_wait(&bars[st], (use - 1) & 1);  // MMAs that read this stage are done
-    float* base = smem + st * kStageFloats;
-    float* a_hi = base;
-    float* a_lo = base + NB * kAFloats;
-    float* b_hi = base + 2 * NB * kAFloats;
-    float* b_lo = b_hi + kBFloats;
+    if (it > 0) umma::mbar_wait(bar, (it - 1) & 1);  // the MMAs that read the stage are done
     store_rows<NB * 128, 128>(pa, a_hi, a_lo, tid);
     store_rows<N, N>(pb, b_hi, b_lo, tid);
-    // software pipeline: the next chunk's global loads are in flight during the barrier / MMA issue / next wait
-    if (c + (int)gridDim.x < nchunks) {
-      prefetch_rows<NB * 128>(pa, XT, ldx, K, (c + gridDim.x) * kWgS, P, tid);
-      prefetch_rows<N>(pb, DYT, ldy, Nvalid, (c + gridDim.x) * kWgS, P, tid);
-    }
     umma::fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -140,17 +136,16 @@ k_wgrad_tc(const float* __restrict__ XT, int ldx, int K, const float* __restrict
           }
         }
       }
-      umma::commit(&bars[st]);
+      umma::commit(bar);
+    }
+    // the next chunk's global loads are in flight while the tensor core works on this one
+    if (c + (int)gridDim.x < nchunks) {
+      prefetch_rows<NB * 128>(pa, XT, ldx, K, (c + gridDim.x) * kWgS, P, tid);
+      prefetch_rows<N>(pb, DYT, ldy, Nvalid, (c + gridDim.x) * kWgS, P, tid);
     }
   }
-  // drain: wait for the last commit on each stage that was used
   if (it > 0) {
-    const uint32_t last = it - 1;
-    umma::mbar_wait(&bars[last & 1], (last >> 1) & 1);
-    if (it > 1) {
-      const uint32_t prev = it - 2;
-      umma::mbar_wait(&bars[prev & 1], (prev >> 1) & 1);
-    }
+    umma::mbar_wait(bar, (it - 1) & 1);
     umma::fence_after_sync();
     // epilogue: warp w -> TMEM lanes 32*(w%4).., column halves split over the two warp groups
     const int q = warp & 3;
@@ -185,11 +180,11 @@ static inline int smc() {
 template <int NB, int N>
 static int launch_wgrad(const float* XT, int ldx, int K, const float* DYT, int ldy, int Nvalid, int Pmax, const int32_t* cnt, float* dw,
                         int dw_ld, cudaStream_t st) {
-  const size_t sm = (size_t)2 * (2 * NB * 128 * kWgS + 2 * N * kWgS) * sizeof(float) + 64;
+  const size_t sm = (size_t)(2 * NB * 128 * kWgS + 2 * N * kWgS) * sizeof(float) + 64;
   cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<NB, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return (int)e;
   const int nchunks = (Pmax + kWgS - 1) / kWgS;
-  const int grid = nchunks < smc() ? nchunks : smc();
+  const int grid = nchunks < 2 * smc() ? nchunks : 2 * smc();   // two CTAs per SM: one converts / issues while the other's loads are in flight
   k_wgrad_tc<NB, N><<<grid, kWgThreads, sm, st>>>(XT, ldx, K, DYT, ldy, Nvalid, Pmax, cnt, dw, dw_ld);
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
