@@ -63,7 +63,8 @@ __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.
 __device__ __forceinline__ float3 vm_group_bwd(const float* __restrict__ plane, const float* __restrict__ line,
                                                float* __restrict__ gplane, float* __restrict__ gline, int C, int W,
                                                const Tap1& tu, const Tap1& tv, const Tap1& tl, int c, float4 g,
-                                               float4* feat = nullptr /* optional: the forward value plane*line of the group */) {
+                                               float4* feat = nullptr /* optional: the forward value plane*line of the group */,
+                                               bool need_gx = true /* false: skip d/d(coords), returns zeros */) {
   const size_t o00 = ((size_t)tv.i0 * W + tu.i0) * C + c, o01 = ((size_t)tv.i0 * W + tu.i1) * C + c;
   const size_t o10 = ((size_t)tv.i1 * W + tu.i0) * C + c, o11 = ((size_t)tv.i1 * W + tu.i1) * C + c;
   const bool b00 = tu.v0 && tv.v0, b01 = tu.v1 && tv.v0, b10 = tu.v0 && tv.v1, b11 = tu.v1 && tv.v1;
@@ -86,12 +87,14 @@ __device__ __forceinline__ float3 vm_group_bwd(const float* __restrict__ plane, 
   if (b11) red_add4(gplane + o11, dp.x * w11, dp.y * w11, dp.z * w11, dp.w * w11);
   if (tl.v0) red_add4(gline + l0, dl.x * tl.r0, dl.y * tl.r0, dl.z * tl.r0, dl.w * tl.r0);
   if (tl.v1) red_add4(gline + l1, dl.x * tl.r1, dl.y * tl.r1, dl.z * tl.r1, dl.w * tl.r1);
-  float3 gx;
-  const float4 dpu = fma4(sub4(P11, P10), tv.r1, mul4(sub4(P01, P00), tv.r0));
-  const float4 dpv = fma4(sub4(P11, P01), tu.r1, mul4(sub4(P10, P00), tu.r0));
-  gx.x = dot4(dp, dpu) * tu.scale;
-  gx.y = dot4(dp, dpv) * tv.scale;
-  gx.z = dot4(dl, sub4(L1, L0)) * tl.scale;
+  float3 gx = make_float3(0.f, 0.f, 0.f);
+  if (need_gx) {
+    const float4 dpu = fma4(sub4(P11, P10), tv.r1, mul4(sub4(P01, P00), tv.r0));
+    const float4 dpv = fma4(sub4(P11, P01), tu.r1, mul4(sub4(P10, P00), tu.r0));
+    gx.x = dot4(dp, dpu) * tu.scale;
+    gx.y = dot4(dp, dpv) * tv.scale;
+    gx.z = dot4(dl, sub4(L1, L0)) * tl.scale;
+  }
   return gx;
 }
 
@@ -226,7 +229,7 @@ __device__ __forceinline__ void scatter_vm_rows(const dynrf_vm_t& vm, const dynr
       float3 r;
       if (Afeat) {   // fused recompute: the taps are loaded once for the scatter and for the forward value
         float4 fv = make_float4(0.f, 0.f, 0.f, 0.f);
-        r = act ? vm_group_bwd(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], C, vm.W[pl], tu, tv, tl, g * 4, gg, &fv)
+        r = act ? vm_group_bwd(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], C, vm.W[pl], tu, tv, tl, g * 4, gg, &fv, gxs != nullptr)
                 : make_float3(0.f, 0.f, 0.f);
         float* fa = Afeat + (size_t)(row_base + coff + g * 4) * LD + m;
         fa[0] = fv.x;

@@ -565,7 +565,7 @@ k_basis_bwd(dynrf_field_cfg_t cfg, dynrf_vm_t vm, dynrf_vm_grad_t gvm, const flo
         acc_store<80, kBT2, kBL2, false>(acc, dAc, 72, tid);
       }
       // one pass over the taps: scatter d(plane*line) and recompute the forward features for the basis weight gradient
-      scatter_vm_rows<kBT2, kBL2>(vm, gvm, scr.xq, 1 << si, 0, dAc, tid, scr.on, scr.gx, Ac);
+      scatter_vm_rows<kBT2, kBL2>(vm, gvm, scr.xq, 1 << si, 0, dAc, tid, scr.on, gcoord ? scr.gx : nullptr, Ac);
       __syncthreads();
       {
         float accB[5][2];
@@ -642,6 +642,10 @@ int dynrf_basis_bwd(const dynrf_field_cfg_t* cfg, int dynamic, const dynrf_vm_t*
                     const int32_t* active_count, float* gbasis_wt, float* gcoord, void* stream) {
   if (!cfg || !app || !gapp || !wbB || !coords || !DFT || !active_idx || !active_count || !gbasis_wt || N <= 0 || S <= 0) return DYNRF_E_ARG;
   if (app->C[0] != 48 || app->C[1] != 12 || app->C[2] != 12) return DYNRF_E_UNSUPPORTED;
+  // planes (x,y) (x,z) (y,z) of one grid
+  if (app->W[1] != app->W[0] || app->W[2] != app->H[0] || app->H[1] != app->L[0] || app->H[2] != app->L[0] || app->L[1] != app->H[0] ||
+      app->L[2] != app->W[0])
+    return DYNRF_E_UNSUPPORTED;
   const int grid = min((N * S + kBT2 - 1) / kBT2, 2 * sm_count());
   cudaError_t e;
   if (dynamic) {
