@@ -169,7 +169,8 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
         taps.t[t][mm] = make_int4(tp.i0 | ((int)tp.v0 << 30), tp.i1 | ((int)tp.v1 << 30), __float_as_int(tp.r0), __float_as_int(tp.r1));
       }
       prod_bar();
-      const bool act = scr.on[m] != 0;
+      const bool act_m = scr.on[m] != 0;
+      const bool act = act_m;
       const uint32_t base = ring.chunk;
       // ---- layer-1 operand chunks (same K order as the forward kernel), streamed to XT
 #pragma unroll 1
@@ -269,6 +270,9 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
 #pragma unroll 1
       for (int tb = 0; tb < 2; ++tb) {
         const uint32_t colbase = 128u + 80u * tb;
+        // a sample whose upstream gradient is exactly zero (relu'd density <= 0: half the samples at initialisation, all of
+        // empty space in a trained scene) has dH = 0, hence d feat = 0: its lookups and reductions are skipped
+        const bool act = act_m && go[tb * kTileM + m] != 0.f;
 #pragma unroll 1
         for (int si = 0; si < 3; ++si) {
           float g0 = 0.f, g1 = 0.f, g2 = 0.f;

@@ -137,6 +137,13 @@ def compare_pass(ref, got, thres=1e-4, check=True):
         assert rep["s_rgb"] <= 1e-4 and rep["d_rgb"] <= 1e-4, rep
         for k in ("rgb_full", "rgb_s", "rgb_d"):
             assert rep[f"o_{k}_rel"] <= TOL_RGB_REL + 1e-4 * (rep["s_mask_flips"] + rep["d_mask_flips"] > 0), rep
-        for k in ("acc_full", "acc_s", "acc_d", "w_full", "w_s", "w_d", "dyn"):
+        for k in ("acc_full", "acc_s", "acc_d", "w_full", "w_s", "dyn"):
             assert rep[f"o_{k}"] <= 5e-5, rep
+        # w_d is divided by its own per-ray sum (renderer.py:252): on a ray whose dynamic weights sum to ~1e-3 a 1e-7 error
+        # in one weight is a 1e-4 error in the normalised one.  Compare after undoing the normalisation.
+        sr = ref["fd"][4].sum(-1, keepdim=True) + 1e-10
+        sg = got["fd"][4].sum(-1, keepdim=True) + 1e-10
+        rep["o_w_d_unnormalised"] = _maxabs(ref["out"][11] * sr, got["out"][11] * sg)
+        assert rep["o_w_d_unnormalised"] <= 2e-5, rep
+        assert rep["o_w_d"] <= 5e-5 + 300 * rep["d_weight"] / float(sr.min()), rep
     return rep
