@@ -261,7 +261,10 @@ int dynrf_pack_sb_umma(const float* w1_density, const float* w1_blending, float*
 int dynrf_dyn_sigma_blend_fwd_tc2(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density, const dynrf_vm_t* blending,
                                   const float* wq, const float* b1cat, const float* w2cat, const float* b2cat,
                                   const float* xyz, const float* xyz_prime, const uint8_t* valid, const float* tfeat, int N,
-                                  int S, float* sigma, float* blend, void* stream);
+                                  int S, float* sigma, float* blend, float* XT_or_null, float* HT_or_null, int ld, void* stream);
+/* XT_or_null / HT_or_null (both or neither): keep the layer-1 inputs X^T [224][ld] (80 position/time rows in engine order,
+ * 72 density features, 72 blending features) and the hidden activations H^T [128][ld] (density | blending, relu'd, zero on
+ * invalid samples) for dynrf_dyn_mlp_bwd_tc; ld >= round_up(N*S,128), multiple of 4. */
 
 /* ---- tensor-core backward of the appearance head on the active samples -----------------------------------
  * dynamic = 1: MLPRender_Fea_late_view of the dynamic field; dynamic = 0: MLPRender_Fea / MLPRender_Fea_TimeEmbedding of the
@@ -317,8 +320,10 @@ int dynrf_pack_sb_bwd(const float* w1_density, const float* w1_blending, float* 
 int dynrf_dyn_mlp_bwd_tc(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density, const dynrf_vm_t* blending,
                          const dynrf_vm_grad_t* gdensity, const dynrf_vm_grad_t* gblending, const float* wq, const float* cst,
                          const float* xyz, const float* xyz_prime, const uint8_t* valid, const float* tfeat, const float* gsigma,
-                         const float* gblend, int N, int S, int ld, float* XT, float* DHT, float* gxp, float* gw2, float* gb1,
-                         float* gb2, void* stream);
+                         const float* gblend, int N, int S, int ld, float* XT, const float* HT_saved_or_null, float* DHT, float* gxp,
+                         float* gw2, float* gb1, float* gb2, void* stream);
+/* HT_saved_or_null != NULL: X^T and H^T were kept by dynrf_dyn_sigma_blend_fwd_tc2 -- layer 1 is not recomputed and XT is only
+ * read by the weight-gradient GEMM afterwards; NULL: layer 1 is recomputed and X^T written here. */
 
 /* Weight-gradient GEMM on tensor cores (3-pass split TF32, fp32 TMEM accumulation):
  *   dw[n * dw_ld + k] += sum_{p < P} XT[k * ldx + p] * DYT[n * ldy + p],  k < K <= 256, n < N <= 128,

@@ -350,7 +350,9 @@ __global__ void __launch_bounds__(kTc3Threads, 1)
 k_dyn_sigma_blend_tc2(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, const float* __restrict__ wq /*kSbWFloats*/,
                       const float* __restrict__ b1cat /*[128]*/, const float* __restrict__ w2cat /*[128]*/, const float* __restrict__ b2cat /*[2]*/,
                       const float* __restrict__ xyz, const float* __restrict__ xyz_prime, const uint8_t* __restrict__ valid,
-                      const float* __restrict__ tfeat, int P, int S, float* __restrict__ sigma, float* __restrict__ blend) {
+                      const float* __restrict__ tfeat, int P, int S, float* __restrict__ sigma, float* __restrict__ blend,
+                      float* __restrict__ XT /*[224][ld] layer-1 inputs, optional*/, float* __restrict__ HT /*[128][ld] relu(layer 1)*/,
+                      int ld) {
   extern __shared__ __align__(128) float smem[];
   float* abuf = smem;
   float* wbuf = abuf + 3 * kOpFloats;
@@ -433,16 +435,19 @@ k_dyn_sigma_blend_tc2(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, co
         float* buf = ring_abuf(ring);
         if (j < 3) {
           const int u0 = j * 5, nu = (j == 2) ? 4 : 5;
-          for (int u = prt; u < nu; u += 4) produce_pos_unit(u0 + u, scr, tfeat, m, buf);
+          for (int u = prt; u < nu; u += 4)
+            produce_pos_unit(u0 + u, scr, tfeat, m, buf, XT ? XT + (size_t)(j * 32) * ld : nullptr, ld, tile * kTileM + m);
         } else {
           const int si = (j - 3) >> 1;
           const bool isbl = ((j - 3) & 1) != 0;
+          const int xrow = (isbl ? 152 : 80) + si * 24;   // XT rows: 80 position/time | 72 density | 72 blending
           {
             const float* pp = isbl ? vbl.plane[0] : vden.plane[0];
             const float* ll = isbl ? vbl.line[0] : vden.line[0];
             float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
             if (act) r = vm_group_f(pp, ll, 16, G[0], load_tap(taps, si, 0, m), load_tap(taps, si, 1, m), load_tap(taps, si, 2, m), prt * 4);
             store_quad(buf, m, prt, r);
+            if (XT) store_quad_g(XT, ld, xrow + prt * 4, tile * kTileM + m, r);
           }
           if (prt < 2) {
             const float* pp = prt == 0 ? (isbl ? vbl.plane[1] : vden.plane[1]) : (isbl ? vbl.plane[2] : vden.plane[2]);
@@ -453,6 +458,7 @@ k_dyn_sigma_blend_tc2(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, co
               r = vm_group_f(pp, ll, 4, prt == 0 ? G[0] : G[1], load_tap(taps, si, prt == 0 ? 0 : 1, m), load_tap(taps, si, 2, m),
                              load_tap(taps, si, prt == 0 ? 1 : 0, m), 0);
             store_quad(buf, m, 4 + prt, r);
+            if (XT) store_quad_g(XT, ld, xrow + 16 + prt * 4, tile * kTileM + m, r);
           }
         }
         umma::fence_async_smem();
@@ -471,12 +477,20 @@ k_dyn_sigma_blend_tc2(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, co
         float r[32];
         umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 32, r);
         float acc = 0.f;
+        const bool on = scr.on[q * 32 + lane] != 0;
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
           const int n = cb * 32 + jj;
-          acc = fmaf(fmaxf(r[jj] + cst[n], 0.f), cst[128 + n], acc);
+          r[jj] = fmaxf(r[jj] + cst[n], 0.f);
+          acc = fmaf(r[jj], cst[128 + n], acc);
         }
         part[cb * kTileM + q * 32 + lane] = acc;
+        if (HT) {   // hidden activations for the backward (zero on samples outside the bounding box)
+#pragma unroll
+          for (int qq = 0; qq < 8; ++qq)
+            store_quad_g(HT, ld, cb * 32 + qq * 4, tile * kTileM + q * 32 + lane,
+                         on ? make_float4(r[qq * 4], r[qq * 4 + 1], r[qq * 4 + 2], r[qq * 4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f));
+        }
       }
       umma::fence_before_sync();
       prod_bar();
@@ -606,10 +620,12 @@ int dynrf_pack_sb_umma(const float* w_den, const float* w_bl, float* wq, void* s
 int dynrf_dyn_sigma_blend_fwd_tc2(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density, const dynrf_vm_t* blending,
                                   const float* wq, const float* b1cat, const float* w2cat, const float* b2cat, const float* xyz,
                                   const float* xyz_prime, const uint8_t* valid, const float* tfeat, int N, int S, float* sigma,
-                                  float* blend, void* stream) {
+                                  float* blend, float* XT, float* HT, int ld, void* stream) {
   if (!cfg || !density || !blending || !wq || !b1cat || !w2cat || !b2cat || !xyz || !xyz_prime || !valid || !tfeat || !sigma || !blend ||
       N <= 0 || S <= 0)
     return DYNRF_E_ARG;
+  if ((XT != nullptr) != (HT != nullptr)) return DYNRF_E_ARG;
+  if (XT && ((ld & 3) || ld < ((N * S + kTileM - 1) / kTileM) * kTileM)) return DYNRF_E_ARG;
   for (int i = 0; i < 3; ++i) {
     const int c = i == 0 ? 16 : 4;
     if (density->C[i] != c || blending->C[i] != c) return DYNRF_E_UNSUPPORTED;
@@ -622,7 +638,7 @@ int dynrf_dyn_sigma_blend_fwd_tc2(const dynrf_field_cfg_t* cfg, const dynrf_vm_t
   const int P = N * S;
   const int grid = min((P + kTileM - 1) / kTileM, sm_count());
   k_dyn_sigma_blend_tc2<<<grid, kTc3Threads, kSb2Smem, S_(stream)>>>(*cfg, *density, *blending, wq, b1cat, w2cat, b2cat, xyz,
-                                                                  xyz_prime, valid, tfeat, P, S, sigma, blend);
+                                                                  xyz_prime, valid, tfeat, P, S, sigma, blend, XT, HT, ld);
   DYNRF_CHECK_LAUNCH();
   return 0;
 }

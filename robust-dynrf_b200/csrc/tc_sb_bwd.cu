@@ -35,7 +35,8 @@ struct SbBwdArgs {
   const float* gsigma;  // [P] d loss / d sigma   (or NULL)
   const float* gblend;  // [P] d loss / d blending (or NULL)
   int P, S, ld;
-  float* XT;    // [225][ld]
+  float* XT;    // [225][ld]   (recompute variant: written here; saved variant: written by the forward, untouched)
+  const float* HT;  // [128][ld] relu(layer 1) saved by the forward (saved variant)
   float* DHT;   // [128][ld]
   float* gxp;   // [P][3] +=
   float* gw2;   // [128] += (density | blending layer-2 weight gradients)
@@ -73,6 +74,10 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float4& r) {
 constexpr size_t kSbbSmem = (size_t)(3 * kOpFloats + 2 * kWSlotFloats + kSbbCst + 4 * kTileM + 2 * kTileM) * sizeof(float) +
                             sizeof(TapsSmemB) + sizeof(TileScratch<kTileM>) + 128;
 
+// SAVED = false: layer 1 is recomputed (gathers, encodings, 9 operand chunks) and X^T is streamed for the weight-gradient GEMM.
+// SAVED = true : the forward kept X^T and H^T (1.4 GB at cfg 2); the tile only forms dH, runs the 4 data-gradient chunks and
+//                scatters.  The path is bound by instruction issue, not by HBM, so trading recompute for 0.5 GB of reads pays.
+template <bool SAVED>
 __global__ void __launch_bounds__(kTc3Threads, 1)
 k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_vm_grad_t gden, dynrf_vm_grad_t gbl, SbBwdArgs a) {
   extern __shared__ __align__(128) float smem[];
@@ -103,23 +108,25 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
   const int P = a.P;
   const int ntiles = (P + kTileM - 1) / kTileM;
   const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const uint32_t total_chunks = (uint32_t)my_tiles * kSbbChunks;
+  constexpr int kC0 = SAVED ? 9 : 0;                 // first chunk of the schedule that this variant runs
+  constexpr int kNC = kSbbChunks - kC0;
+  const uint32_t total_chunks = (uint32_t)my_tiles * kNC;
   const float* b1cat = cst;
   const float* w2cat = cst + 128;
   const float* b2cat = cst + 256;
 
   if (warp == kProdThreads / 32) {
     if (lane == 0 && total_chunks > 0) {
-      ring_prefetch_w(ring, 0, a.wq + sbb_woff(0), 2u * sbb_n(0) * sbb_rows(0) * 4u);
+      ring_prefetch_w(ring, 0, a.wq + sbb_woff(kC0), 2u * sbb_n(kC0) * sbb_rows(kC0) * 4u);
       for (uint32_t c = 0; c < total_chunks; ++c) {
-        const int j = (int)(c % kSbbChunks);
+        const int j = kC0 + (int)(c % kNC);
         ring.chunk = c;
         umma::mbar_wait(&bar_full[c % 3], (c / 3) & 1);
         if (j < 3) ring_issue<128>(ring, sbb_rows(j), 0u, j == 0);
         else if (j < 9) ring_issue<64>(ring, sbb_rows(j), ((j - 3) & 1) ? 64u : 0u, false);
         else ring_issue<80>(ring, sbb_rows(j), j < 11 ? 128u : 208u, j == 9 || j == 11);
         if (c + 1 < total_chunks) {
-          const int nj = (j + 1) % kSbbChunks;
+          const int nj = kC0 + (int)((c + 1) % kNC);
           ring_prefetch_w(ring, c + 1, a.wq + sbb_woff(nj), 2u * sbb_n(nj) * sbb_rows(nj) * 4u);
         }
       }
@@ -174,7 +181,7 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
       const uint32_t base = ring.chunk;
       // ---- layer-1 operand chunks (same K order as the forward kernel), streamed to XT
 #pragma unroll 1
-      for (int j = 0; j < 9; ++j) {
+      for (int j = 0; j < (SAVED ? 0 : 9); ++j) {
         ring_wait_free(ring);
         float* buf = ring_abuf(ring);
         if (j < 3) {
@@ -206,18 +213,21 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
         arrive();
       }
       // ---- epilogue A: layer 2, activation derivatives, dH -> data-gradient operand chunks, DHT, register reductions
-      wait_chunk(base + 8);
+      if (!SAVED) wait_chunk(base + 8);
       {
         float h[32];
-        umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 32, h);
         const bool on = scr.on[em] != 0;
         float po = 0.f;
+        if (SAVED) {
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const int n = cb * 32 + jj;
-          h[jj] = on ? fmaxf(h[jj] + b1cat[n], 0.f) : 0.f;
-          po = fmaf(h[jj], w2cat[n], po);
+          for (int jj = 0; jj < 32; ++jj) h[jj] = __ldg(a.HT + (size_t)(cb * 32 + jj) * ld + i0g + em);   // already relu'd and masked
+        } else {
+          umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 32, h);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) h[jj] = on ? fmaxf(h[jj] + b1cat[cb * 32 + jj], 0.f) : 0.f;
         }
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) po = fmaf(h[jj], w2cat[cb * 32 + jj], po);
         part[cb * kTileM + em] = po;
         prod_bar();
         if (tid < 2 * kTileM) {
@@ -266,7 +276,7 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
         }
       }
       // ---- epilogue B: d feat (TMEM) -> plane / line gradients + coordinate gradients
-      wait_chunk(base + 12);
+      wait_chunk(base + kNC - 1);
 #pragma unroll 1
       for (int tb = 0; tb < 2; ++tb) {
         const uint32_t colbase = 128u + 80u * tb;
@@ -401,8 +411,8 @@ int dynrf_pack_sb_bwd(const float* w_den, const float* w_bl, float* wq, int32_t*
 int dynrf_dyn_mlp_bwd_tc(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density, const dynrf_vm_t* blending,
                          const dynrf_vm_grad_t* gdensity, const dynrf_vm_grad_t* gblending, const float* wq, const float* cst,
                          const float* xyz, const float* xyz_prime, const uint8_t* valid, const float* tfeat, const float* gsigma,
-                         const float* gblend, int N, int S, int ld, float* XT, float* DHT, float* gxp, float* gw2, float* gb1,
-                         float* gb2, void* stream) {
+                         const float* gblend, int N, int S, int ld, float* XT, const float* HT_saved, float* DHT, float* gxp,
+                         float* gw2, float* gb1, float* gb2, void* stream) {
   if (!cfg || !density || !blending || !gdensity || !gblending || !wq || !cst || !xyz || !xyz_prime || !valid || !tfeat || !XT || !DHT ||
       !gxp || !gw2 || !gb1 || !gb2 || N <= 0 || S <= 0 || (ld & 3) || ld < ((N * S + kTileM - 1) / kTileM) * kTileM)
     return DYNRF_E_ARG;
@@ -412,11 +422,20 @@ int dynrf_dyn_mlp_bwd_tc(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density
     if (density->H[i] != blending->H[i] || density->W[i] != blending->W[i] || density->L[i] != blending->L[i]) return DYNRF_E_UNSUPPORTED;
   }
   if ((uintptr_t)wq & 15) return DYNRF_E_ALIGN;
-  cudaError_t e = cudaFuncSetAttribute(k_dyn_mlp_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSbbSmem);
-  if (e != cudaSuccess) return (int)e;
-  SbBwdArgs a{wq, cst, xyz, xyz_prime, valid, tfeat, gsigma, gblend, N * S, S, ld, XT, DHT, gxp, gw2, gb1, gb2};
+  SbBwdArgs a{wq, cst, xyz, xyz_prime, valid, tfeat, gsigma, gblend, N * S, S, ld, XT, HT_saved, DHT, gxp, gw2, gb1, gb2};
   const int grid = min((N * S + kTileM - 1) / kTileM, sm_count());
-  k_dyn_mlp_bwd_tc<<<grid, kTc3Threads, kSbbSmem, reinterpret_cast<cudaStream_t>(stream)>>>(*cfg, *density, *blending, *gdensity, *gblending, a);
+  cudaError_t e;
+  if (HT_saved) {
+    e = cudaFuncSetAttribute(k_dyn_mlp_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSbbSmem);
+    if (e != cudaSuccess) return (int)e;
+    k_dyn_mlp_bwd_tc<true><<<grid, kTc3Threads, kSbbSmem, reinterpret_cast<cudaStream_t>(stream)>>>(*cfg, *density, *blending, *gdensity,
+                                                                                                   *gblending, a);
+  } else {
+    e = cudaFuncSetAttribute(k_dyn_mlp_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSbbSmem);
+    if (e != cudaSuccess) return (int)e;
+    k_dyn_mlp_bwd_tc<false><<<grid, kTc3Threads, kSbbSmem, reinterpret_cast<cudaStream_t>(stream)>>>(*cfg, *density, *blending, *gdensity,
+                                                                                                    *gblending, a);
+  }
   DYNRF_CHECK_LAUNCH();
   return 0;
 }

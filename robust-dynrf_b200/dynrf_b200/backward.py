@@ -390,10 +390,12 @@ class _SbBwdState:
             self.key = key
         return self
 
-    def scratch(self, ld, dev):
+    def scratch(self, ld, dev, need_xt=True):
         b = self.bufs.get(ld)
         if b is None:
-            b = self.bufs[ld] = dict(XT=torch.empty(225, ld, device=dev), DHT=torch.empty(128, ld, device=dev))
+            b = self.bufs[ld] = dict(DHT=torch.empty(128, ld, device=dev))
+        if need_xt and "XT" not in b:
+            b["XT"] = torch.empty(225, ld, device=dev)
         return b
 
 
@@ -407,14 +409,19 @@ def _dyn_mlp_bwd_tc(m, cfg, r, vden, vbl, gden, gbl, gsig, gblend, gxp, n, s):
     dev = gxp.device
     P = n * s
     ld = ops.round_up(P, 128)
-    b = st.scratch(ld, dev)
+    saved = r.get("sb_saved")
+    if saved is not None and r.get("sb_ld") != ld:
+        saved = None
+    b = st.scratch(ld, dev, need_xt=saved is None)
+    xt = saved["XT"] if saved is not None else b["XT"]
     gsmall = torch.zeros(258, device=dev)      # gw2 (128) | gb1 (128) | gb2 (2)
     L.check(lib.dynrf_dyn_mlp_bwd_tc(C.byref(cfg), C.byref(vden), C.byref(vbl), C.byref(gden), C.byref(gbl), _p(st.wq), _p(st.cst),
                                      _p(r["xyz"]), _p(r["xyz_prime"]), _p(r["valid"]), _p(r["tfeat"]), _p(gsig), _p(gblend), n, s, ld,
-                                     _p(b["XT"]), _p(b["DHT"]), _p(gxp), _p(gsmall), _p(gsmall[128:]), _p(gsmall[256:]), _stream()),
+                                     _p(xt), _p(saved["HT"]) if saved is not None else None, _p(b["DHT"]), _p(gxp), _p(gsmall),
+                                     _p(gsmall[128:]), _p(gsmall[256:]), _stream()),
             "dynrf_dyn_mlp_bwd_tc")
     dwf = torch.zeros(128, 224, device=dev)
-    L.check(lib.dynrf_wgrad_gemm(_p(b["XT"]), ld, 224, _p(b["DHT"]), ld, 128, P, None, _p(dwf), 224, _stream()), "dynrf_wgrad_gemm")
+    L.check(lib.dynrf_wgrad_gemm(_p(xt), ld, 224, _p(b["DHT"]), ld, 128, P, None, _p(dwf), 224, _stream()), "dynrf_wgrad_gemm")
     dw_d = torch.empty(64, 152, device=dev)
     dw_b = torch.empty(64, 152, device=dev)
     dw_d[:, :72] = dwf[:64, 80:152]

@@ -123,14 +123,14 @@ PROTOTYPES = {
     "dynrf_app_fwd_tc": [_cfg, _I, _vm, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P],
     "dynrf_sb_bwd_wfloats": [],
     "dynrf_pack_sb_bwd": [_P, _P, _P, _P, _P],
-    "dynrf_dyn_mlp_bwd_tc": [_cfg, _vm, _vm, _vg, _vg, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "dynrf_dyn_mlp_bwd_tc": [_cfg, _vm, _vm, _vg, _vg, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "dynrf_basis_bwd": [_cfg, _I, _vm, _vg, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "dynrf_wgrad_gemm": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _I, _P],
     "dynrf_selftest_umma_gemm": [_P, _P, _I, _I, _I, _P, _P],
     "dynrf_pack_linear_umma": [_P, _P, _I, _I, _P, _P, _P],
     "dynrf_sb_umma_floats": [],
     "dynrf_pack_sb_umma": [_P, _P, _P, _P],
-    "dynrf_dyn_sigma_blend_fwd_tc2": [_cfg, _vm, _vm, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P],
+    "dynrf_dyn_sigma_blend_fwd_tc2": [_cfg, _vm, _vm, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P],
     "dynrf_warp_fwd_tc": [_cfg, _P, _I, _I, _P, _ul, _ul, _ly, _P, _P],
     "dynrf_dyn_sigma_blend_fwd_tc": [_cfg, _vm, _vm, _ul, _ly, _ul, _ly, _P, _P, _P, _P, _I, _I, _P, _P, _P],
 }

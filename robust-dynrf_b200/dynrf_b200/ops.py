@@ -157,6 +157,8 @@ USE_TC = True
 # Bumped whenever parameters may have changed without their autograd version counters moving (a CUDA-graph replay of a
 # train step updates the weights in place on the device): every packed-operand cache includes it in its key.
 PARAM_EPOCH = [0]
+# keep layer inputs / hidden activations of the tensor-core forward kernels for their backward instead of recomputing them
+SAVE_ACTIVATIONS = True
 TC_SB_VERSION = 2
 
 
@@ -184,6 +186,14 @@ class PackedSigmaBlend:
         self.w2cat = torch.empty(128, device=dev)
         self.b2cat = torch.empty(2, device=dev)
         self._key = None
+        self._saved = {}
+
+    def saved_buffers(self, ld, dev):
+        """X^T [225][ld] / H^T [128][ld] scratch shared by the forward (writer) and the backward of the same step."""
+        b = self._saved.get(ld)
+        if b is None:
+            b = self._saved[ld] = dict(XT=torch.empty(225, ld, device=dev), HT=torch.empty(128, ld, device=dev))
+        return b
 
     def refresh(self):
         m = self.m
@@ -361,6 +371,7 @@ def dynamic_forward_raw(m, rays, ts, xyz, z_vals, valid, ray_type, save_feat=Fal
     blend = torch.empty(n, s, device=dev)
     vden = vm_struct(m.density_plane, m.density_line)
     vbl = vm_struct(m.blending_plane, m.blending_line)
+    sb_saved, sb_ld = None, 0
     if USE_TC:
         ul = umma_layers(m, ("layer3", "layer4", "d1", "b1"))
         L.check(lib.dynrf_warp_fwd_tc(C.byref(cfg), _p(xyz), n, s, _p(tfeat), C.byref(ul["layer3"]), C.byref(ul["layer4"]),
@@ -370,9 +381,16 @@ def dynamic_forward_raw(m, rays, ts, xyz, z_vals, valid, ray_type, save_feat=Fal
             if psb is None:
                 psb = m.__dict__["_packed_sb"] = PackedSigmaBlend(m)
             psb.refresh()
+            if save_feat and SAVE_ACTIVATIONS:
+                # layer-1 inputs and hidden activations of the density / blending MLPs, kept for the backward: the step is
+                # bound by instruction issue, not by HBM, so 1.4 GB of extra stores is cheaper than recomputing layer 1
+                sb_ld = round_up(n * s, 128)
+                sb_saved = psb.saved_buffers(sb_ld, dev)
             L.check(lib.dynrf_dyn_sigma_blend_fwd_tc2(C.byref(cfg), C.byref(vden), C.byref(vbl), _p(psb.wq), _p(psb.b1cat),
                                                       _p(psb.w2cat), _p(psb.b2cat), _p(xyz), _p(xyz_prime), _p(valid_u8),
-                                                      _p(tfeat), n, s, _p(sigma), _p(blend), _stream()),
+                                                      _p(tfeat), n, s, _p(sigma), _p(blend),
+                                                      _p(sb_saved["XT"]) if sb_saved else None,
+                                                      _p(sb_saved["HT"]) if sb_saved else None, sb_ld, _stream()),
                     "dynrf_dyn_sigma_blend_fwd_tc2")
         else:
             L.check(lib.dynrf_dyn_sigma_blend_fwd_tc(C.byref(cfg), C.byref(vden), C.byref(vbl), C.byref(ul["d1"]),
@@ -403,7 +421,7 @@ def dynamic_forward_raw(m, rays, ts, xyz, z_vals, valid, ray_type, save_feat=Fal
                                       C.byref(ly["h3"]), _p(rays), _p(xyz), _p(xyz_prime), _p(tfeat), n, s, _p(idx), _p(cnt),
                                       _p(rgb), _p(featT), ldf, _stream()), "dynrf_dyn_app_fwd")
     return dict(sigma=sigma, blend=blend, weight=weight, dists=dists, rgb=rgb, xyz_prime=xyz_prime, tfeat=tfeat, idx=idx,
-                cnt=cnt, rays=rays, ts=ts, xyz=xyz, z_vals=z_vals, valid=valid_u8, featT=featT, ldf=ldf)
+                cnt=cnt, rays=rays, ts=ts, xyz=xyz, z_vals=z_vals, valid=valid_u8, featT=featT, ldf=ldf, sb_saved=sb_saved, sb_ld=sb_ld)
 
 
 def composite_raw(rgb_s, sigma_s, rgb_d, sigma_d, dists, blending, z_vals, rays, white_bg: bool, ray_type: str):

@@ -89,6 +89,12 @@ def test_parameter_gradients(ray_type, static_mode, grid, n, s):
 
 
 @gpu
+def test_parameter_gradients_full_grid():
+    """cfg 2's 331x368x220 grid, 256 rays x 256 samples (the oracle's autograd finishes in seconds at this batch)."""
+    test_parameter_gradients("ndc", "MLP_Fea", [331, 368, 220], 256, 256)
+
+
+@gpu
 @pytest.mark.parametrize("ray_type,static_mode", [("ndc", "MLP_Fea"), ("contract", "MLP_Fea_TimeEmbedding")])
 def test_static_ray_gradients(ray_type, static_mode):
     """PASS 5 shape: rays carry grad -> xyz -> static field; d loss / d rays (pose / focal chain)."""
