@@ -142,7 +142,7 @@ __device__ __forceinline__ int tap_key(const Tap1& t, bool act) {
 __device__ __forceinline__ float3 vm_group_bwd_agg(const float* __restrict__ plane, const float* __restrict__ line,
                                                    float* __restrict__ gplane, float* __restrict__ gline, int C, int W,
                                                    const Tap1& tu, const Tap1& tv, const Tap1& tl, int c, float4 g, bool act,
-                                                   int lane) {
+                                                   int lane, float4* feat = nullptr, bool need_gx = true) {
   const size_t o00 = ((size_t)tv.i0 * W + tu.i0) * C + c, o01 = ((size_t)tv.i0 * W + tu.i1) * C + c;
   const size_t o10 = ((size_t)tv.i1 * W + tu.i0) * C + c, o11 = ((size_t)tv.i1 * W + tu.i1) * C + c;
   const bool b00 = act && tu.v0 && tv.v0, b01 = act && tu.v1 && tv.v0, b10 = act && tu.v0 && tv.v1, b11 = act && tu.v1 && tv.v1;
@@ -159,6 +159,7 @@ __device__ __forceinline__ float3 vm_group_bwd_agg(const float* __restrict__ pla
   float4 l = mul4(L0, tl.r0);
   l = fma4(L1, tl.r1, l);
   const float4 dp = act ? mul44(g, l) : zero4(), dl = act ? mul44(g, p) : zero4();
+  if (feat) *feat = act ? mul44(p, l) : zero4();
   {
     const WarpRuns ru = warp_runs(tap_key(tu, act), tap_key(tv, act), lane);
     const float4 d00 = seg_reduce4(b00 ? mul4(dp, w00) : zero4(), ru), d01 = seg_reduce4(b01 ? mul4(dp, w01) : zero4(), ru);
@@ -178,27 +179,34 @@ __device__ __forceinline__ float3 vm_group_bwd_agg(const float* __restrict__ pla
       if (c1) red_add4(gline + l1, e1.x, e1.y, e1.z, e1.w);
     }
   }
-  float3 gx;
-  const float4 dpu = fma4(sub4(P11, P10), tv.r1, mul4(sub4(P01, P00), tv.r0));
-  const float4 dpv = fma4(sub4(P11, P01), tu.r1, mul4(sub4(P10, P00), tu.r0));
-  gx.x = dot4(dp, dpu) * tu.scale;
-  gx.y = dot4(dp, dpv) * tv.scale;
-  gx.z = dot4(dl, sub4(L1, L0)) * tl.scale;
+  float3 gx = make_float3(0.f, 0.f, 0.f);
+  if (need_gx) {
+    const float4 dpu = fma4(sub4(P11, P10), tv.r1, mul4(sub4(P01, P00), tv.r0));
+    const float4 dpv = fma4(sub4(P11, P01), tu.r1, mul4(sub4(P10, P00), tu.r0));
+    gx.x = dot4(dp, dpu) * tu.scale;
+    gx.y = dot4(dp, dpv) * tv.scale;
+    gx.z = dot4(dl, sub4(L1, L0)) * tl.scale;
+  }
   return gx;
 }
 
-// Compile-time choice between the two scatters.  Measured on B200 (cfg2, synthetic rays, random-init fields): the L2
-// reduction units are NOT the limiter of any backward kernel (169 M red sectors in 3.3 ms), and the extra shuffles cost
-// 2-8 % -- so the plain scatter is the default.  Scenes with long coherent runs can flip this.
-constexpr bool kAggScatter = false;
+// Compile-time choice between the two scatters.  Measured on B200 (cfg 2): once layer 1 is no longer recomputed the
+// backward tile kernels are dominated by this scatter and the L2 reduction rate (~45 red sectors / clk chip-wide) becomes the
+// limiter: aggregation takes k_dyn_mlp_bwd_tc from 2.77 to 2.52 ms and k_static_density_bwd from 0.29 to 0.24 ms even with
+// the incoherent taps of a randomly initialised warp field (with layer-1 recompute in the same kernel it was a 3 % loss).
+constexpr bool kAggScatter = true;
 __device__ __forceinline__ float3 vm_group_bwd_w(const float* __restrict__ plane, const float* __restrict__ line,
                                                  float* __restrict__ gplane, float* __restrict__ gline, int C, int W, const Tap1& tu,
-                                                 const Tap1& tv, const Tap1& tl, int c, float4 g, bool act, int lane) {
+                                                 const Tap1& tv, const Tap1& tl, int c, float4 g, bool act, int lane,
+                                                 float4* feat = nullptr, bool need_gx = true) {
   if constexpr (kAggScatter) {
-    return vm_group_bwd_agg(plane, line, gplane, gline, C, W, tu, tv, tl, c, g, act, lane);
+    return vm_group_bwd_agg(plane, line, gplane, gline, C, W, tu, tv, tl, c, g, act, lane, feat, need_gx);
   } else {
-    if (!act) return make_float3(0.f, 0.f, 0.f);
-    return vm_group_bwd(plane, line, gplane, gline, C, W, tu, tv, tl, c, g);
+    if (!act) {
+      if (feat) *feat = zero4();
+      return make_float3(0.f, 0.f, 0.f);
+    }
+    return vm_group_bwd(plane, line, gplane, gline, C, W, tu, tv, tl, c, g, feat, need_gx);
   }
 }
 
@@ -228,9 +236,9 @@ __device__ __forceinline__ void scatter_vm_rows(const dynrf_vm_t& vm, const dynr
       const float4 gg = make_float4(a[0], a[LD], a[2 * LD], a[3 * LD]);
       float3 r;
       if (Afeat) {   // fused recompute: the taps are loaded once for the scatter and for the forward value
-        float4 fv = make_float4(0.f, 0.f, 0.f, 0.f);
-        r = act ? vm_group_bwd(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], C, vm.W[pl], tu, tv, tl, g * 4, gg, &fv, gxs != nullptr)
-                : make_float3(0.f, 0.f, 0.f);
+        float4 fv;
+        r = vm_group_bwd_w(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], C, vm.W[pl], tu, tv, tl, g * 4, gg, act, tid & 31, &fv,
+                           gxs != nullptr);
         float* fa = Afeat + (size_t)(row_base + coff + g * 4) * LD + m;
         fa[0] = fv.x;
         fa[LD] = fv.y;
