@@ -191,18 +191,6 @@ __device__ __forceinline__ int pos_src_index(int r) {  // row 0..79 of the posit
 }
 
 
-// backward tap: forward tap + validity + d(index)/d(coord)
-struct TapB {
-  int i0, i1;
-  float w0, w1;  // 1 - frac, frac (raw)
-  float scale;
-  bool v0, v1;
-};
-__device__ __forceinline__ TapB tapb(float x, int n, int s) {
-  const Tap1 t = make_tap(x, n, s);
-  return TapB{t.i0, t.i1, t.r0, t.r1, t.scale, t.v0, t.v1};
-}
-
 // v[c] holds this lane's value of column c; returns (in lane L) the sum over the 32 lanes of column L
 __device__ __forceinline__ float warp_col_reduce32(float (&v)[32], int lane) {
 #pragma unroll
