@@ -39,7 +39,7 @@ N_SAMPLES = 256
 WORKLOAD = "cfg2: Nvidia.txt Balloon1 shape, static+dynamic VM fields grid [331,368,220], 4096 NDC rays x 256 samples per GPU"
 METRIC = "rays/sec (train step)"
 BYTES_PER_SAMPLE_K1 = 588  # 576 B gathered + 12 B written, samples generated in-kernel
-BYTES_PER_SAMPLE_SBB = 3 * 3456 + 1412 + 57  # k_dyn_mlp_bwd_tc, see DESIGN.md 6
+BYTES_PER_SAMPLE_SBB = 2 * 3456 + 512 + 512 + 57  # k_dyn_mlp_bwd_tc<SAVED>, see DESIGN.md 6
 
 
 def peaks():
@@ -328,15 +328,15 @@ def main():
                                   "ms_per_launch": ksb_ms, "peak_source": pk["src"],
                                   "note": "useful fp32-equivalent flops (the tensor cores execute 3x this as TF32 passes); bf16 dense peak quoted as the denominator the task names"},
             "roofline_dominant": None if not kdom else {
-                "kernel": "k_dyn_mlp_bwd_tc (backward of a16+a17: recompute + dgrad on tcgen05, scatter from TMEM, operand streams for the wgrad GEMM)",
+                "kernel": "k_dyn_mlp_bwd_tc<SAVED> (backward of a16+a17: dH from the saved activations, dgrad on tcgen05, warp-aggregated scatter from TMEM)",
                 "bound": "hbm", "achieved": N_RAYS * N_SAMPLES * BYTES_PER_SAMPLE_SBB / (sum(kdom) / len(kdom) * 1e-3) / 1e9,
                 "peak": pk["hbm"], "unit": "GB/s",
                 "frac": N_RAYS * N_SAMPLES * BYTES_PER_SAMPLE_SBB / (sum(kdom) / len(kdom) * 1e-3) / 1e9 / pk["hbm"],
-                "traffic": 1.80e9, "ms_per_launch": sum(kdom) / len(kdom), "bytes_per_sample": BYTES_PER_SAMPLE_SBB,
+                "traffic": None, "ms_per_launch": sum(kdom) / len(kdom), "bytes_per_sample": BYTES_PER_SAMPLE_SBB,
                 "peak_source": pk["src"],
-                "note": "algorithmic bytes: 3456 gathered + 3456 re-read by the scatter + 3456 reduced + 1412 streamed (X^T 225 rows, dH^T 128 rows) + 57 per-sample I/O; "
-                        "the 21 MB of tables are L2-resident, DRAM traffic (ncu, profiles/r01_ncu_full_bwd_summary.json) is 1.8 GB/launch, almost all of it the operand streams; "
-                        "the kernel is bound by producer-side instruction issue, not by HBM"},
+                "note": "algorithmic bytes per sample: 3456 re-read by the scatter + 3456 reduced + 512 read (H^T) + 512 written (dH^T) + 57 of per-sample I/O; "
+                        "the 21 MB of tables are L2-resident, so DRAM sees ~1 GB/launch of activation streams; the kernel is bound by the L2 reduction rate "
+                        "and instruction issue, not by HBM"},
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": int(rays_pin.numel() * 4 + ts_pin.numel() * 4 + target_pin.numel() * 4),
                     "d2h_bytes_per_step": int(out_pin.numel() * 4), "ms_per_step": t2_ms / args.steps},
             "gpu_launches": launches, "clocks": clocks,

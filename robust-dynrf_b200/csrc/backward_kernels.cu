@@ -356,7 +356,7 @@ k_static_density_bwd(dynrf_field_cfg_t cfg, dynrf_vm_t vm, dynrf_vm_grad_t gvm, 
     const Tap1 tu = make_tap(xn[u], vm.W[pl], 1), tv = make_tap(xn[v], vm.H[pl], 1), tl = make_tap(xn[l], vm.L[pl], 1);
     for (int c = 0; c < vm.C[pl]; c += 4) {
       const float3 r = vm_group_bwd_w(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], vm.C[pl], vm.W[pl], tu, tv, tl, c, g4, act,
-                                        threadIdx.x & 31);
+                                      threadIdx.x & 31, nullptr, gxyz != nullptr);
       gacc[u] += r.x;
       gacc[v] += r.y;
       gacc[l] += r.z;
