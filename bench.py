@@ -152,6 +152,8 @@ def run_reference(args):
         return
     mode = "train" if args.mode in ("auto", "train") else "fwd"
     n = 1024
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    torch.set_num_threads(max(torch.get_num_threads(), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
     cores = torch.get_num_threads()
     ref = CpuReference(n, mode)
     ts = ref.time(args.steps, args.warmup)
