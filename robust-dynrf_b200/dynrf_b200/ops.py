@@ -186,14 +186,6 @@ class PackedSigmaBlend:
         self.w2cat = torch.empty(128, device=dev)
         self.b2cat = torch.empty(2, device=dev)
         self._key = None
-        self._saved = {}
-
-    def saved_buffers(self, ld, dev):
-        """X^T [225][ld] / H^T [128][ld] scratch shared by the forward (writer) and the backward of the same step."""
-        b = self._saved.get(ld)
-        if b is None:
-            b = self._saved[ld] = dict(XT=torch.empty(225, ld, device=dev), HT=torch.empty(128, ld, device=dev))
-        return b
 
     def refresh(self):
         m = self.m
@@ -384,8 +376,9 @@ def dynamic_forward_raw(m, rays, ts, xyz, z_vals, valid, ray_type, save_feat=Fal
             if save_feat and SAVE_ACTIVATIONS:
                 # layer-1 inputs and hidden activations of the density / blending MLPs, kept for the backward: the step is
                 # bound by instruction issue, not by HBM, so 1.4 GB of extra stores is cheaper than recomputing layer 1
+                # allocated per forward call (not cached on the model): several forwards may be alive before their backwards run
                 sb_ld = round_up(n * s, 128)
-                sb_saved = psb.saved_buffers(sb_ld, dev)
+                sb_saved = dict(XT=torch.empty(225, sb_ld, device=dev), HT=torch.empty(128, sb_ld, device=dev))
             L.check(lib.dynrf_dyn_sigma_blend_fwd_tc2(C.byref(cfg), C.byref(vden), C.byref(vbl), _p(psb.wq), _p(psb.b1cat),
                                                       _p(psb.w2cat), _p(psb.b2cat), _p(xyz), _p(xyz_prime), _p(valid_u8),
                                                       _p(tfeat), n, s, _p(sigma), _p(blend),

@@ -195,3 +195,33 @@ def test_reference_golden_gradients(golden_case):
             if abs(got - want) > 2e-3 * max(want, 1e-6):
                 bad[f"{tag}:{name}"] = (got, want)
     assert not bad, bad
+
+
+@gpu
+def test_interleaved_forwards_keep_their_own_saved_state():
+    """Two forwards alive at once (the reference's train loop runs several passes before one backward): the activations a
+    forward keeps for its backward must not be shared between calls."""
+    import renderer as R
+
+    case_a = H.build_pair([30, 34, 26], 160, 64, seed=21)
+    case_b = H.build_pair([30, 34, 26], 160, 64, seed=22, sd_static=case_a["sd_static"], sd_dynamic=case_a["sd_dynamic"])
+
+    def run(interleave):
+        static, dyn = H.native_models(case_a, DEV)
+        outs = []
+        for c in ([case_a, case_b] if interleave else [case_a]):
+            rays, ts = c["rays"].to(DEV), c["ts"].to(DEV)
+            xyz, z, valid = R.sampleXYZ(dyn, rays, 64, "ndc", False)
+            fs = static(rays, ts, None, xyz, z, valid, ray_type="ndc")
+            fd = dyn(rays, ts, None, xyz, z, valid, ray_type="ndc")
+            outs.append(R.raw2outputs(fs[6], fs[7], fd[6], fd[7], fd[9], fd[2], fd[8], rays, False, "ndc"))
+        o = outs[0]
+        (o[0].sum() + 0.5 * o[8].sum() + o[4].sum()).backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.clone() for m_ in (static, dyn) for n, p in m_.named_parameters() if p.grad is not None}
+
+    alone, mixed = run(False), run(True)
+    assert alone.keys() == mixed.keys()
+    for k in alone:
+        ok, emax, e2 = _grad_ok(mixed[k].cpu(), alone[k].cpu(), loose=1e-3, l2=1e-4)
+        assert ok, (k, emax, e2)
