@@ -13,7 +13,10 @@ One "step" = one pass of the hot path over one ray batch:
   --mode fwd   : sampleXYZ(is_train) -> static field -> dynamic field -> raw2outputs   (evaluation pass)
   --mode train : the PASS-1 structure of the reference train loop (train.py:1092-1162): the pass above with
                  autograd, an MSE loss on the three composited colours, backward to every dynamic + static
-                 parameter (and, for N>1, one NCCL all-reduce of the gradients).
+                 parameter, one Adam update (and, for N>1, one NCCL all-reduce of the flat gradient buffer).
+The step is replayed as a CUDA graph after three eager warm-up steps (--no-graph launches it eagerly): at ~16 ms of GPU
+work per step the ~100 kernel launches + ~300 small tensor ops of the eager step cost as much host time as the GPU needs.
+`--impl reference` runs the SAME step (train: forward + autograd backward + Adam) of the CPU oracle port on all host threads.
 `value` times the step with inputs resident in HBM; `e2e` times the same step through the public Python
 API starting from PINNED HOST ray buffers (H2D inside the timed region) and ending with the composited
 per-ray maps back on the host (D2H inside).  Between timed iterations a 512 MiB buffer is rewritten to
