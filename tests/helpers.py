@@ -33,21 +33,24 @@ def synth_rays(n, ray_type, gen, spread=0.1):
 
 
 def build_pair(grid, n_rays, n_samples, ray_type="ndc", static_mode="MLP_Fea", seed=0, sd_static=None, sd_dynamic=None,
-               rays=None, ts=None, aabb=None, near_far=None):
+               rays=None, ts=None, aabb=None, near_far=None, act="relu", density_shift=-10.0):
     gen = torch.Generator().manual_seed(seed)
     if aabb is None:
         aabb = torch.tensor(NDC_AABB if ray_type == "ndc" else CONTRACT_AABB)
     if near_far is None:
         near_far = (0.0, 1.0) if ray_type == "ndc" else (0.0, 256.0)
-    cs = O.FieldCfg(aabb=aabb, near_far=tuple(near_far), shadingMode=static_mode, fea_pe=2, dynamic=False)
-    cd = O.FieldCfg(aabb=aabb, near_far=tuple(near_far), shadingMode="MLP_Fea_late_view", fea_pe=0, dynamic=True)
+    cs = O.FieldCfg(aabb=aabb, near_far=tuple(near_far), shadingMode=static_mode, fea_pe=2, dynamic=False, fea2denseAct=act,
+                    density_shift=density_shift)
+    cd = O.FieldCfg(aabb=aabb, near_far=tuple(near_far), shadingMode="MLP_Fea_late_view", fea_pe=0, dynamic=True, fea2denseAct=act,
+                    density_shift=density_shift)
     if sd_static is None:
         sd_static = O.init_state_dict(cs, grid, gen)
         sd_dynamic = O.init_state_dict(cd, grid, gen)
     if rays is None:
         rays, ts = synth_rays(n_rays, ray_type, gen)
     return dict(grid=list(grid), aabb=aabb, near_far=tuple(near_far), ray_type=ray_type, static_mode=static_mode, cs=cs,
-                cd=cd, sd_static=sd_static, sd_dynamic=sd_dynamic, rays=rays, ts=ts, n_samples=n_samples)
+                cd=cd, sd_static=sd_static, sd_dynamic=sd_dynamic, rays=rays, ts=ts, n_samples=n_samples, act=act,
+                density_shift=density_shift)
 
 
 def native_models(case, device):
@@ -55,7 +58,8 @@ def native_models(case, device):
 
     dev = torch.device(device)
     aabb = case["aabb"].to(dev)
-    kw = dict(COMMON, near_far=list(case["near_far"]))
+    kw = dict(COMMON, near_far=list(case["near_far"]), fea2denseAct=case.get("act", "relu"),
+              density_shift=case.get("density_shift", -10.0))
     static = T.TensorVMSplit(aabb, case["grid"], 12, dev, shadingMode=case["static_mode"], fea_pe=2, **kw)
     dyn = T.TensorVMSplit_TimeEmbedding(aabb, case["grid"], 12, dev, shadingMode="MLP_Fea_late_view", fea_pe=0, **kw)
     static.load_state_dict(case["sd_static"])

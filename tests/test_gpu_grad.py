@@ -61,7 +61,10 @@ def _native_full(case, rays_grad=False):
     ("ndc", "MLP_Fea", [40, 44, 36], 200, 150),
 ])
 def test_parameter_gradients(ray_type, static_mode, grid, n, s):
-    case = H.build_pair(grid, n, s, ray_type=ray_type, static_mode=static_mode, seed=7 * n + s)
+    _check_parameter_gradients(H.build_pair(grid, n, s, ray_type=ray_type, static_mode=static_mode, seed=7 * n + s))
+
+
+def _check_parameter_gradients(case):
     ss, sd, _, fs, fd, o = _oracle_full(case)
     shapes = [t.shape for t in o] + [fd[5].shape, fd[2].shape, fs[4].shape]
     ws = _loss_weights(shapes, 99)
@@ -86,6 +89,13 @@ def test_parameter_gradients(ray_type, static_mode, grid, n, s):
     bad = {k: v for k, v in worst.items() if not v[0]}
     print(sorted(((k, v[1], v[2]) for k, v in worst.items()), key=lambda kv: -kv[1])[:8])
     assert not bad, bad
+
+
+@gpu
+def test_parameter_gradients_softplus():
+    """softplus density activation: sigma' = sigmoid(f + shift) in both density backward kernels."""
+    case = H.build_pair([24, 26, 22], 400, 96, ray_type="ndc", static_mode="MLP_Fea", seed=41, act="softplus", density_shift=-1.5)
+    _check_parameter_gradients(case)
 
 
 @gpu

@@ -152,3 +152,13 @@ def test_tensor_core_path_matches_simt_path():
         d = float((a["fd"][i] - b["fd"][i]).abs().max())
         print(name, d)
         assert d <= 5e-6, (name, d)
+
+
+@gpu
+@pytest.mark.parametrize("ray_type", ["ndc", "contract"])
+def test_softplus_density_activation(ray_type):
+    """fea2denseAct="softplus" (the constructor default of the reference; the shipped configs use relu)."""
+    case = H.build_pair([28, 30, 26], 200, 72, ray_type=ray_type, static_mode="MLP_Fea" if ray_type == "ndc" else "MLP_Fea_TimeEmbedding",
+                        seed=31, act="softplus", density_shift=-1.5)
+    rep = H.compare_pass(H.oracle_pass(case), H.native_pass(case, DEV))
+    print(rep)
