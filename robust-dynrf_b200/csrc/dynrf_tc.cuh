@@ -129,40 +129,44 @@ __device__ __forceinline__ void produce_pos_unit(int u, const TileScratch<kTileM
 #undef DYNRF_PUT
 
 struct Ring {
-  uint64_t* bar_free;  // [3] operand buffer consumed (MMAs of the chunk that used it completed)
-  uint64_t* bar_w;     // [2] weight slot landed
-  float* abuf;         // 3 x kOpFloats
-  float* wbuf;         // 2 x kWSlotFloats
+  uint64_t* bar_free;  // [nbuf] operand buffer consumed (MMAs of the chunk that used it completed)
+  uint64_t* bar_w;     // [nw] weight slot landed
+  float* abuf;         // nbuf x kOpFloats
+  float* wbuf;         // nw x wslot
   uint32_t chunk;      // running chunk counter, identical in every thread
   uint32_t tmem;
   uint32_t wslot = kWSlotFloats;  // floats per weight slot
+  uint32_t nbuf = 3;              // operand buffers
+  uint32_t nw = 2;                // weight slots: chunk c's weights are requested while chunk c - (nw - 1) is being issued
 };
 
 __device__ __forceinline__ void ring_wait_free(const Ring& r) {
-  const uint32_t b = r.chunk % 3, u = r.chunk / 3;
+  const uint32_t b = r.chunk % r.nbuf, u = r.chunk / r.nbuf;
   if (u > 0) umma::mbar_wait_backoff(&r.bar_free[b], (u - 1) & 1);
 }
-__device__ __forceinline__ float* ring_abuf(const Ring& r) { return r.abuf + (size_t)(r.chunk % 3) * kOpFloats; }
+__device__ __forceinline__ float* ring_abuf(const Ring& r) { return r.abuf + (size_t)(r.chunk % r.nbuf) * kOpFloats; }
 
-// tid 0: weights of chunk `c` (global blob) -> slot c & 1.  The slot was last read by chunk c-2.
+// tid 0: weights of chunk `c` (global blob) -> slot c % nw.  The slot was last read by chunk c - nw.
 __device__ __forceinline__ void ring_prefetch_w(const Ring& r, uint32_t c, const float* blob, uint32_t bytes) {
-  if (c >= 2) {
-    const uint32_t pc = c - 2;
-    umma::mbar_wait(&r.bar_free[pc % 3], (pc / 3) & 1);
+  if (c >= r.nw) {
+    const uint32_t pc = c - r.nw;
+    umma::mbar_wait(&r.bar_free[pc % r.nbuf], (pc / r.nbuf) & 1);
   }
-  mbar_expect_tx(&r.bar_w[c & 1], bytes);
-  tma_load_1d(r.wbuf + (size_t)(c & 1) * r.wslot, blob, bytes, &r.bar_w[c & 1]);
+  const uint32_t slot = c % r.nw;
+  mbar_expect_tx(&r.bar_w[slot], bytes);
+  tma_load_1d(r.wbuf + (size_t)slot * r.wslot, blob, bytes, &r.bar_w[slot]);
 }
 
 // tid 0: wait for this chunk's weights, issue the 3-pass MMAs, commit to the operand buffer's barrier
 template <int N>
 __device__ __forceinline__ void ring_issue(const Ring& r, int rows, uint32_t col0, bool first) {
   const uint32_t c = r.chunk;
-  umma::mbar_wait(&r.bar_w[c & 1], (c >> 1) & 1);
+  const uint32_t slot = c % r.nw, buf = c % r.nbuf;
+  umma::mbar_wait(&r.bar_w[slot], (c / r.nw) & 1);
   umma::fence_after_sync();
   const uint32_t idesc = umma::make_idesc_tf32(kTileM, N);
-  const uint32_t sa_hi = umma::smem_u32(r.abuf + (size_t)(c % 3) * kOpFloats), sa_lo = sa_hi + kOpLo * 4;
-  const uint32_t sb_hi = umma::smem_u32(r.wbuf + (size_t)(c & 1) * r.wslot), sb_lo = sb_hi + N * rows * 4;
+  const uint32_t sa_hi = umma::smem_u32(r.abuf + (size_t)buf * kOpFloats), sa_lo = sa_hi + kOpLo * 4;
+  const uint32_t sb_hi = umma::smem_u32(r.wbuf + (size_t)slot * r.wslot), sb_lo = sb_hi + N * rows * 4;
 #pragma unroll
   for (int ps = 0; ps < 3; ++ps) {
     const uint32_t sa = (ps == 2) ? sa_lo : sa_hi;
@@ -173,7 +177,7 @@ __device__ __forceinline__ void ring_issue(const Ring& r, int rows, uint32_t col
       umma::mma_tf32(r.tmem + col0, da, db, idesc, (!first || ps > 0 || j > 0) ? 1u : 0u);
     }
   }
-  umma::commit(&r.bar_free[c % 3]);
+  umma::commit(&r.bar_free[buf]);
 }
 
 // row 0..79 of the position/time operand block (this engine's K order, see tc_kernels.cu) -> index 0..79 in the

@@ -74,7 +74,11 @@ struct HeadBwdArgs {
   float* gvd;   // [N][3] += d loss / d viewdir through layer 1 (static MLP_Fea head, optional)
 };
 
-constexpr size_t kHbSmem = (size_t)(3 * kOpFloats + 2 * kHbWSlot + kHbCst + 4 * 3 * kTileM + 3 * kTileM) * sizeof(float) +
+// The tensor-core warp spends ~0.2 us on the MMAs of a chunk but a 32-40 KB weight blob takes ~1 us to arrive from L2, and the
+// 16-17 chunks of a tile are consumed back to back: with one chunk of weight look-ahead the kernel ran at the weight latency.
+// Three weight slots (two chunks of look-ahead) and two operand buffers fit the same shared memory.
+constexpr uint32_t kHbBufs = 2, kHbSlots = 3;
+constexpr size_t kHbSmem = (size_t)(kHbBufs * kOpFloats + kHbSlots * kHbWSlot + kHbCst + 4 * 3 * kTileM + 3 * kTileM) * sizeof(float) +
                            sizeof(TileScratch<kTileM>) + 128;
 
 template <bool DYN>
@@ -83,19 +87,19 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
   constexpr int kL2 = HB::kNL1, kD2 = HB::kNL1 + 4, kD1 = HB::kNL1 + 8;  // first chunk of each group
   extern __shared__ __align__(128) float smem[];
   float* abuf = smem;
-  float* wbuf = abuf + 3 * kOpFloats;
-  float* cst = wbuf + 2 * kHbWSlot;
+  float* wbuf = abuf + kHbBufs * kOpFloats;
+  float* cst = wbuf + kHbSlots * kHbWSlot;
   float* part = cst + kHbCst;       // [4][3][128] partial output dots
   float* go = part + 4 * 3 * kTileM;  // [3][128] d loss / d (pre-sigmoid output)
   TileScratch<kTileM>& scr = *reinterpret_cast<TileScratch<kTileM>*>(go + 3 * kTileM);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(&scr) + sizeof(TileScratch<kTileM>));
-  uint64_t* bar_free = bars;
-  uint64_t* bar_w = bars + 3;
-  uint64_t* bar_full = bars + 5;
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_free = bars;      // [kHbBufs]
+  uint64_t* bar_w = bars + 3;     // [kHbSlots]
+  uint64_t* bar_full = bars + 7;  // [kHbBufs]
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 10);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < 5; ++i) umma::mbar_init(&bars[i], 1);
+    for (int i = 0; i < 7; ++i) umma::mbar_init(&bars[i], 1);
     for (int i = 0; i < 3; ++i) umma::mbar_init(&bar_full[i], kProdThreads / 32);
     umma::fence_mbar_init();
   }
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  Ring ring{bar_free, bar_w, abuf, wbuf, 0u, *tslot, (uint32_t)kHbWSlot};
+  Ring ring{bar_free, bar_w, abuf, wbuf, 0u, *tslot, (uint32_t)kHbWSlot, kHbBufs, kHbSlots};
   const int count = *a.active_count;
   const int ntiles = (count + kTileM - 1) / kTileM;
   const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -118,19 +122,22 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
   if (warp == kProdThreads / 32) {
     // ===================== tensor-core warp =====================
     if (lane == 0 && total_chunks > 0) {
-      ring_prefetch_w(ring, 0, a.wq + HB::woff(0), 2u * HB::n(0) * HB::rows(0) * 4u);
+      for (uint32_t c = 0; c + 1 < kHbSlots && c < total_chunks; ++c) {
+        const int j0 = (int)(c % HB::kChunks);
+        ring_prefetch_w(ring, c, a.wq + HB::woff(j0), 2u * HB::n(j0) * HB::rows(j0) * 4u);
+      }
       for (uint32_t c = 0; c < total_chunks; ++c) {
         const int j = (int)(c % HB::kChunks);
         ring.chunk = c;
-        umma::mbar_wait(&bar_full[c % 3], (c / 3) & 1);
+        umma::mbar_wait(&bar_full[c % kHbBufs], (c / kHbBufs) & 1);
         if (j < kL2) ring_issue<128>(ring, HB::rows(j), 0u, j == 0);
         else if (j < kD2) ring_issue<128>(ring, 32, 128u, j == kL2);
         else if (j < kD1) ring_issue<128>(ring, 32, 256u, j == kD2);
         else if (DYN) ring_issue<32>(ring, 32, 384u, j == kD1);
         else ring_issue<160>(ring, 32, 0u, j == kD1);  // acc1 / acc2 are dead by now (see epilogue 3)
-        if (c + 1 < total_chunks) {
-          const int nj = (j + 1) % HB::kChunks;
-          ring_prefetch_w(ring, c + 1, a.wq + HB::woff(nj), 2u * HB::n(nj) * HB::rows(nj) * 4u);
+        if (c + kHbSlots - 1 < total_chunks) {
+          const int nj = (int)((c + kHbSlots - 1) % HB::kChunks);
+          ring_prefetch_w(ring, c + kHbSlots - 1, a.wq + HB::woff(nj), 2u * HB::n(nj) * HB::rows(nj) * 4u);
         }
       }
     }
@@ -149,13 +156,13 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
     for (int i = 0; i < 3; ++i) acc_b3[i] = 0.f;
 
     auto wait_chunk = [&](uint32_t c) {
-      umma::mbar_wait_backoff(&bar_free[c % 3], (c / 3) & 1);
+      umma::mbar_wait_backoff(&bar_free[c % kHbBufs], (c / kHbBufs) & 1);
       umma::fence_after_sync();
     };
     auto arrive = [&]() {
       umma::fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_full[ring.chunk % 3]);
+      if (lane == 0) mbar_arrive(&bar_full[ring.chunk % kHbBufs]);
       ring.chunk++;
     };
 
