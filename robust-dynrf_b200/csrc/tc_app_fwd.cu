@@ -213,7 +213,10 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
         }
       }
       // ---- epilogue A: basis output (27 features) -> head input operand
-      wait_chunk(base + AF::kNB - 1);
+      // wait on the most recently produced chunk (for the dynamic head: the last position chunk, which shares its operand buffer
+      // with the last basis chunk): tcgen05 operations retire in order, so this also covers the basis GEMM, and a wait on an
+      // older chunk of the same buffer could alias with the next phase of its barrier
+      wait_chunk(base + AF::kNB - 1 + (DYN ? 3 : 0));
       {
         float f[8];
         tmem_ld8(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 8, f);
