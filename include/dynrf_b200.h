@@ -157,7 +157,7 @@ int dynrf_dyn_app_fwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* app, const
                       const int32_t* active_idx, const int32_t* active_count, float* rgb, float* featT_or_null, int ldf,
                       void* stream);
 /* featT [32][ldf] (optional): the 27 basis outputs of active sample j at column j, feature-major, rows 27..31 zero;
- * consumed by dynrf_dyn_head_bwd_tc.  ldf >= round_up(N*S, 128). */
+ * consumed by dynrf_head_bwd_tc.  ldf >= round_up(N*S, 128). */
 
 /* ---- a19: two-field compositing (renderer.raw2outputs, renderer.py:173-315) ----------------
  * white_bg: the reference's host-side coin (is_train && rand<0.5), decided by the caller.
