@@ -105,6 +105,11 @@ class Step:
         import gc
 
         gc.collect()   # drop autograd graphs (and their AccumulateGrad nodes, which remember a stream) of earlier eager steps
+        # p.grad lives in the flat buffer created on the caller's stream while the warm-up / capture run on a side stream: the
+        # mismatch is intended (both are joined before and after), so the per-backward warning about it is noise
+        _warn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if _warn is not None:
+            _warn(False)
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         ins = (rays.clone(), ts.clone(), None if target is None else target.clone())
