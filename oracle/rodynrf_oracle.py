@@ -133,7 +133,7 @@ def sample_ray_contracted(
         edges = edges.clone()
         edges[:, :-1] += (u * ((2.0 - near) / n_in))[:, :-1]
     z_in = (edges[:, 1:] + edges[:, :-1]) * 0.5
-    r = torch.arange(n_out + 1)[None].float()
+    r = torch.arange(n_out + 1, device=rays_o.device)[None].float()
     if is_train:
         u = torch.rand_like(r) if jitter_outer is None else jitter_outer.to(r)
         r[:, :-1] += u[:, :-1]
@@ -298,9 +298,10 @@ def field_forward(cfg: FieldCfg, sd, rays: Tensor, ts: Tensor, xyz: Tensor, z_va
     viewdirs = viewdirs.view(-1, 1, 3).expand(xyz.shape)
     t_tiled = torch.tile(ts.unsqueeze(-1), (1, s))
 
-    sigma = torch.zeros(n, s)
-    rgb = torch.zeros(n, s, 3)
-    blending = torch.zeros(n, s, 1)
+    dev = xyz.device   # CPU in the tests; bench.py's `ref_cuda_eager` leg runs the same restatement on the GPU
+    sigma = torch.zeros(n, s, device=dev)
+    rgb = torch.zeros(n, s, 3, device=dev)
+    blending = torch.zeros(n, s, 1, device=dev)
     xn = normalize_coord(cfg, xyz)
     if ray_valid.any():
         if cfg.dynamic:

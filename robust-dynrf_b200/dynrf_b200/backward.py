@@ -210,6 +210,13 @@ class DynamicFieldFn(torch.autograd.Function):
     def backward(ctx, gblend, gweight, gxyzp, grgb, gsigma, gdists):
         lib = L.load()
         m, rt, r = ctx.model, ctx.ray_type, ctx.r
+        if ctx.needs_input_grad[4] and any(g is not None for g in (gblend, gweight, gxyzp, grgb, gsigma)):
+            # nothing silently detaches: d(dynamic outputs)/d(xyz) is not produced by the backward kernels (the reference train
+            # loop only ever multiplies it by zero: train.py:1094-1159 detaches the rays of pass 1, :1812,2216,2281 use *_s only)
+            raise NotImplementedError(
+                "dynrf_b200: gradients of the DYNAMIC field's outputs with respect to the sample positions (xyz_sampled) are not "
+                "implemented; pass xyz_sampled.detach() to the dynamic model (the static field provides d/dxyz for pose / focal "
+                "optimisation).")
         cfg = m.native_cfg(rt)
         n, s = r["sigma"].shape
         dev = r["sigma"].device
@@ -283,6 +290,7 @@ class _HeadBwdState:
         lib = L.load()
         dev = m.basis_mat.weight.device
         self.dyn = 1 if m.is_dynamic else 0
+        ops.check_tc_shapes(m)
         self.xrows = lib.dynrf_head_bwd_xrows(self.dyn)
         self.wq = torch.empty(lib.dynrf_head_bwd_wfloats(self.dyn), device=dev)
         self.cst = torch.empty(lib.dynrf_head_bwd_cst_floats(), device=dev)
@@ -296,6 +304,7 @@ class _HeadBwdState:
         l1, l2, l3 = tbl["h1"], tbl["h2"], tbl["h3"]
         key = (ops.PARAM_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias))
         if key != self.key:
+            ops.check_tc_shapes(m)
             with torch.no_grad():
                 L.check(L.load().dynrf_pack_head_bwd(self.dyn, m.head_mode, _p(_f32c(l1.weight.detach())), _p(_f32c(l2.weight.detach())),
                                                      _p(self.wq), _p(self.colmap), _stream()), "dynrf_pack_head_bwd")
@@ -471,8 +480,6 @@ class CompositeFn(torch.autograd.Function):
                                         _p(blending), _p(z_vals), _p(rays), n, s, _p(go), _p(gwf), _p(gws), _p(gwd), _p(g_rgb_s),
                                         _p(g_ss), _p(g_rgb_d), _p(g_sd), _p(g_di), _p(g_bl), _p(g_rays), _stream()),
                 "dynrf_composite_bwd")
-        if rays.shape[1] != 6:
-            g_rays = None
         return g_rgb_s, g_ss, g_rgb_d, g_sd, g_di, g_bl, None, g_rays, None, None
 
 
@@ -516,12 +523,20 @@ def train_fwd_bwd(step, rays, ts, target):
     if getattr(step, "opt", None) is None:
         _train_setup(step)
     step.flat_grad.zero_()
-    xyz, z, valid = R.sampleXYZ(dyn, rays, step.s, step.rt, getattr(step, "jitter", True))
-    fs = static(rays, ts, None, xyz, z, valid, is_train=True, ray_type=step.rt, N_samples=step.s)
-    fd = dyn(rays, ts, None, xyz, z, valid, is_train=True, ray_type=step.rt, N_samples=step.s)
+    rays_s = rays
+    if getattr(step, "rays_grad", False):
+        # pose / focal optimisation (cfg 3/4): the rays carry requires_grad; as in the reference's passes 5-9 the gradient reaches
+        # them through the STATIC field (sample positions, view direction, dists); the dynamic field sees detached rays
+        # (train.py:1094-1159 detaches them in pass 1, and only the *_s outputs of the pose passes are used: train.py:1812)
+        rays_s = rays.detach().clone().requires_grad_(True)
+    xyz, z, valid = R.sampleXYZ(dyn, rays_s, step.s, step.rt, getattr(step, "jitter", True))
+    fs = static(rays_s, ts, None, xyz, z, valid, is_train=True, ray_type=step.rt, N_samples=step.s)
+    fd = dyn(rays, ts, None, xyz.detach(), z, valid, is_train=True, ray_type=step.rt, N_samples=step.s)
     o = R.raw2outputs(fs[6], fs[7], fd[6], fd[7], fd[9], fd[2], fd[8], rays, False, step.rt)
     loss = ((o[0] - target) ** 2).mean() + ((o[4] - target) ** 2).mean() + ((o[8] - target) ** 2).mean()
     loss.backward()
+    if rays_s is not rays:
+        step.rays_grad_out = rays_s.grad
     out = torch.cat((o[0], o[1][:, None], o[2][:, None], o[4], o[5][:, None], o[6][:, None], o[8], o[9][:, None],
                      o[10][:, None], o[12][:, None]), -1).detach()
     return out

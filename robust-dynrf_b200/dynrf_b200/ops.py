@@ -203,6 +203,34 @@ class PackedSigmaBlend:
         return self
 
 
+_HEAD_K1 = {L.HEAD_FEA: 138, L.HEAD_FEA_TIMEEMB: 135, L.HEAD_FEA_LATE_VIEW: 107}
+
+
+def check_tc_shapes(m) -> None:
+    """The tensor-core kernels are compiled for the shapes every shipped config uses (density / blending C=[16,4,4],
+    appearance C=[48,12,12], app_dim 27, featureC 128, view_pe 0, fea_pe 2 static / 0 dynamic).  The pack entry points take raw
+    pointers, so anything else must fail HERE, loudly, instead of reading weights with the wrong row stride."""
+    tbl = m._layer_table()
+    l1, l2, l3 = tbl["h1"], tbl["h2"], tbl["h3"]
+    k1 = _HEAD_K1[m.head_mode]
+    nstr = 3 if m.is_dynamic else 1
+    want = {
+        "appearance_n_comp": (list(m.app_n_comp), [48, 12, 12]),
+        "density_n_comp": (list(m.density_n_comp) if m.is_dynamic else [16, 4, 4], [16, 4, 4]),   # static density is shape-generic
+        "basis_mat.weight": (tuple(m.basis_mat.weight.shape), (27, 72 * nstr)),
+        "renderModule layer 1": (tuple(l1.weight.shape), (128, k1)),
+        "renderModule layer 2": (tuple(l2.weight.shape), (128, 128)),
+        "renderModule output layer": (tuple(l3.weight.shape), (3, 128 if m.head_mode == L.HEAD_FEA else 131)),
+    }
+    bad = {k: v for k, v in want.items() if v[0] != v[1]}
+    if bad:
+        raise NotImplementedError(
+            "dynrf_b200: the tensor-core kernels support the hyper-parameters of the shipped configs only "
+            "(app_dim=27, featureC=128, view_pe=0, fea_pe=2 static / 0 dynamic, C=[16,4,4]/[48,12,12]); got "
+            + ", ".join(f"{k}={v[0]} (need {v[1]})" for k, v in bad.items())
+            + ".  Set dynrf_b200.ops.USE_TC = False to run the shape-generic fp32 SIMT kernels.")
+
+
 class PackedAppFwd:
     """Operands of dynrf_app_fwd_tc for one field: packed split-TF32 weights (basis_mat, head layers 1-2) and the
     constant block [b1 | b2 | W3[:, :128]^T | W3[:, 128:131]^T (zeros without a late view input) | b3]."""
@@ -210,6 +238,7 @@ class PackedAppFwd:
     def __init__(self, m):
         self.m = m
         lib = L.load()
+        check_tc_shapes(m)
         dev = m.basis_mat.weight.device
         self.dyn = 1 if m.is_dynamic else 0
         self.wq = torch.empty(lib.dynrf_app_fwd_wfloats(self.dyn), device=dev)
@@ -223,6 +252,7 @@ class PackedAppFwd:
         ps = [m.basis_mat.weight, l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias]
         key = (PARAM_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in ps)
         if key != self._key:
+            check_tc_shapes(m)
             with torch.no_grad():
                 L.check(L.load().dynrf_pack_app_fwd(self.dyn, m.head_mode, _p(_f32c(ps[0].detach())), _p(_f32c(ps[1].detach())),
                                                     _p(_f32c(ps[3].detach())), _p(self.wq), _stream()), "dynrf_pack_app_fwd")
@@ -420,6 +450,9 @@ def dynamic_forward_raw(m, rays, ts, xyz, z_vals, valid, ray_type, save_feat=Fal
 def composite_raw(rgb_s, sigma_s, rgb_d, sigma_d, dists, blending, z_vals, rays, white_bg: bool, ray_type: str):
     lib = L.load()
     _require_cuda(rgb_s, sigma_s, rgb_d, sigma_d, dists, blending, z_vals, rays)
+    if rays.dim() != 2 or rays.shape[1] != 6:
+        # the kernels index o_z / d_z as rays[n*6+2], rays[n*6+5] (the reference reads rays_chunk[..., 2] + rays_chunk[..., -1])
+        raise ValueError(f"raw2outputs: rays_chunk must be [N,6] (origin, direction); got {tuple(rays.shape)} -- pass rays[:, :6]")
     args = [_f32c(t) for t in (rgb_s, sigma_s, rgb_d, sigma_d, dists, blending, z_vals, rays)]
     n, s = args[1].shape
     dev = args[1].device

@@ -30,13 +30,15 @@ class Step:
     work per step the Python / launch overhead is of the same size.  With world > 1 the collectives stay eager between
     two graphs (forward+backward | optimizer)."""
 
-    def __init__(self, static, dyn, n_samples, ray_type, mode, world=1, graph=False, jitter=True):
+    def __init__(self, static, dyn, n_samples, ray_type, mode, world=1, graph=False, jitter=True, rays_grad=False):
         if mode == "train" and not backward_available():
             raise RuntimeError("train mode needs the backward kernels (dynrf_b200.backward)")
         self.static, self.dyn, self.s, self.rt, self.mode, self.world = static, dyn, n_samples, ray_type, mode, world
         self.gather_buf = None
         self.use_graph = graph
         self.jitter = jitter    # stratified-sampling jitter (is_train of renderer.sampleXYZ)
+        self.rays_grad = rays_grad   # train mode: rays carry requires_grad (pose / focal gradient through the static field)
+        self.rays_grad_out = None
         self._g = None          # (inputs, graphs, outputs) once captured
         self.launches_per_step = None
 
@@ -133,6 +135,8 @@ class Step:
             with torch.cuda.graph(g2, pool=g1.pool(), stream=side):
                 self._finish()
         self._g = (ins, g1, g2, out, fused)
+        if _warn is not None:
+            _warn(True)   # restore the process-wide default
 
     def _replay(self, rays, ts, target):
         ins, g1, g2, out, _ = self._g
@@ -149,6 +153,8 @@ class Step:
         return out
 
     def __call__(self, rays, ts, target, fused=True):
+        """-> per-ray maps [N*world, 16].  With graph=True and world == 1 the returned tensor is the graph's static output
+        buffer: the next call overwrites it (clone it to keep it)."""
         if self.mode == "train":
             fused = False   # the train step always goes through the public API
         if self.use_graph:

@@ -25,7 +25,8 @@ class Golden:
         self.meta = ast.literal_eval(str(self.raw["meta"])) if "meta" in self.raw else {}
 
     def t(self, key):
-        return torch.from_numpy(np.ascontiguousarray(self.raw[key]))
+        a = self.raw[key]
+        return torch.from_numpy(np.ascontiguousarray(a)).reshape(a.shape)   # ascontiguousarray promotes 0-d to 1-d
 
     def sd(self, which):
         pre = f"sd_{which}/"
