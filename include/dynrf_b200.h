@@ -335,6 +335,40 @@ int dynrf_wgrad_gemm(const float* XT, int ldx, int K, const float* DYT, int ldy,
 /* Self-test of the tcgen05 tile-GEMM building block: C[128][N] = A[128][K] x B[N][K]^T, N in {32,64,128},
  * passes = 1 (TF32) or 3 (split TF32, ~fp32 accuracy).  Used by tests/test_gpu_umma.py. */
 int dynrf_selftest_umma_gemm(const float* A, const float* B, int K, int N, int passes, float* C, void* stream);
+
+/* ---- rows next to the ray-march path -----------------------------------------------------------
+ * a4: TensorBase.sample_ray (models/tensorBase.py:501-522): aabb entry distance + fixed-step marching.
+ *     jitter: [N] uniforms (is_train) or NULL.  Outputs xyz [N][S][3], z_vals [N][S] (per ray), valid [N][S]. */
+int dynrf_sample_ray(const dynrf_field_cfg_t* cfg, const float* rays, int N, int S, float step_size, const float* jitter,
+                     float* xyz, float* z_vals, uint8_t* valid, void* stream);
+/* f1: fused ray generation (train.py:96-103, 1062-1077; dataLoader/ray_utils.py:53-90, 115-140): flat pixel ids [B] (int64,
+ *     id = view*H*W + row*W + col) + camera-to-world matrices mtx [F][3][4] (camera.pose_to_mtx of the 9-D poses) + focal [1]
+ *     (device scalar) -> rays [B][6]; ndc != 0 applies ndc_rays_blender2 with `near`.  The backward accumulates into
+ *     gmtx [F][3][4] and gfocal [1] (caller zeroes both).
+ *     Instead of ids, explicit sub-pixel coordinates uv [B][2] = (x, y) and camera indices view [B] (int64) may be given
+ *     (ids == NULL): the flow-displaced rays of train.py:1433-1455. */
+int dynrf_raygen_fwd(const int64_t* ids_or_null, const float* uv_or_null, const int64_t* view_or_null, int B, const float* mtx, int F,
+                     const float* focal, int H, int W, int ndc, float near_, float* rays, void* stream);
+int dynrf_raygen_bwd(const int64_t* ids_or_null, const float* uv_or_null, const int64_t* view_or_null, int B, const float* mtx, int F,
+                     const float* focal, int H, int W, int ndc, float near_, const float* grays, float* gmtx, float* gfocal,
+                     void* stream);
+/* f2: the S-reduction of renderer.render_3d_point (renderer.py:1335-1338): pm[n] = sum_s w[n][s] * moved[n][s],
+ *     acc[n] = sum_s w[n][s] with moved = pts (+ sf, the scene flow) (clamped to [lo,hi] when clamp != 0, train.py:1374-1378).
+ *     Backward: gw [N][S] = gpm[n] . moved + gacc[n] (gacc may be NULL), gmoved [N][S][3] = w * gpm[n] (0 where clamped). */
+int dynrf_weighted_point_fwd(const float* w, const float* pts, const float* sf_or_null, int clamp, float lo, float hi, int N, int S,
+                             float* pm, float* acc, void* stream);
+int dynrf_weighted_point_bwd(const float* w, const float* pts, const float* sf_or_null, int clamp, float lo, float hi, int N, int S,
+                             const float* gpm, const float* gacc_or_null, float* gw_or_null, float* gmoved_or_null, void* stream);
+/* f3: total variation (utils.TVLoss, utils.py:157-181) of up to 6 channel-last tensors [H][W][C] in one launch:
+ *     sums[2t] += sum (x[h+1]-x[h])^2, sums[2t+1] += sum (x[w+1]-x[w])^2 (double, caller zeroes); if g[t] != NULL it is
+ *     OVERWRITTEN with ch[t] * d(sums[2t])/dx + cw[t] * d(sums[2t+1])/dx.  Host pointers to arrays of length n. */
+int dynrf_tv_fused(int n, const float* const* x, float* const* g_or_null, const int32_t* C, const int32_t* H, const int32_t* W,
+                   const float* ch, const float* cw, double* sums, void* stream);
+/* f3: density_L1 / blending_L1 (models/tensoRF.py:80-98, 378-416) without the dense C x Gy x Gx x Gz product:
+ *     sum_out[0] += sum_{x,y,z} |act(sum_c plane_i (x) line_i)| (double, caller zeroes; the caller divides by Gx*Gy*Gz);
+ *     if g != NULL the gradient of that SUM is accumulated into g (caller zeroes).  C must be [16,4,4]. */
+int dynrf_dense_l1(const dynrf_vm_t* vm, int act, float shift, double* sum_out, const dynrf_vm_grad_t* g_or_null, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

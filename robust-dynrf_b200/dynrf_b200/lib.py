@@ -14,7 +14,7 @@ PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # robust
 CSRC = os.path.join(PKG_ROOT, "csrc")
 LIB_DIR = os.path.join(PKG_ROOT, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdynrf_b200.so")
-SOURCES = ["ray_kernels.cu", "field_kernels.cu", "backward_kernels.cu", "selftest.cu", "tc_kernels.cu", "wgrad_gemm.cu", "tc_bwd_kernels.cu", "tc_sb_bwd.cu", "tc_app_fwd.cu"]
+SOURCES = ["ray_kernels.cu", "field_kernels.cu", "backward_kernels.cu", "selftest.cu", "tc_kernels.cu", "wgrad_gemm.cu", "tc_bwd_kernels.cu", "tc_sb_bwd.cu", "tc_app_fwd.cu", "extras_kernels.cu"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -132,6 +132,14 @@ PROTOTYPES = {
     "dynrf_pack_sb_umma": [_P, _P, _P, _P],
     "dynrf_dyn_sigma_blend_fwd_tc2": [_cfg, _vm, _vm, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P],
     "dynrf_warp_fwd_tc": [_cfg, _P, _I, _I, _P, _ul, _ul, _ly, _P, _P],
+    # rows next to the path (a4, f1-f3)
+    "dynrf_sample_ray": [_cfg, _P, _I, _I, _F, _P, _P, _P, _P, _P],
+    "dynrf_raygen_fwd": [_P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _F, _P, _P],
+    "dynrf_raygen_bwd": [_P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _P],
+    "dynrf_weighted_point_fwd": [_P, _P, _P, _I, _F, _F, _I, _I, _P, _P, _P],
+    "dynrf_weighted_point_bwd": [_P, _P, _P, _I, _F, _F, _I, _I, _P, _P, _P, _P, _P],
+    "dynrf_tv_fused": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "dynrf_dense_l1": [_vm, _I, _F, _P, _vg, _P],
     "dynrf_dyn_sigma_blend_fwd_tc": [_cfg, _vm, _vm, _ul, _ly, _ul, _ly, _P, _P, _P, _P, _I, _I, _P, _P, _P],
 }
 

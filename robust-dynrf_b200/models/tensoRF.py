@@ -2,8 +2,8 @@
 TensorVMSplit_TimeEmbedding (dynamic) parameter containers with the reference's constructor
 signature, attribute names, state_dict keys and optimizer-group order (models/tensoRF.py:11-61,
 277-376).  Feature lookups / MLPs on the ray-march path run in libdynrf_b200.so via
-TensorBase.forward; the regularisers, coarse-to-fine upsampling and the scene-flow MLP (rows
-f2-f4 of SURVEY.md 8f, "next") are plain PyTorch on the same channel-last parameters.
+TensorBase.forward; the TV / L1 regularisers run as streaming kernels (row f3, dynrf_b200/extras.py); coarse-to-fine
+upsampling, vector_comp_diffs and the scene-flow MLP are plain PyTorch on the same channel-last parameters.
 """
 import torch
 import torch.nn as nn
@@ -26,15 +26,14 @@ def _offdiag_mean_abs(lines):
     return total
 
 
-def _dense_vm(planes, lines):
-    """sum_c plane (x) line as a dense [Gx,Gy,Gz] volume (what density_L1 materialises, :80-98)."""
-    p0, p1, p2 = (p[0] for p in planes)       # (C,Gy,Gx) (C,Gz,Gx) (C,Gz,Gy)
-    l0, l1, l2 = (l[0, :, :, 0] for l in lines)  # (C,Gz) (C,Gy) (C,Gx)
-    return (torch.einsum("cyx,cz->xyz", p0, l0) + torch.einsum("czx,cy->xyz", p1, l1)
-            + torch.einsum("czy,cx->xyz", p2, l2))
-
-
 def _tv(reg, planes, lines):
+    """TV_loss_* (reference models/tensoRF.py:100-116, 419-444).  `reg` is the caller's regulariser; the reference always passes
+    utils.TVLoss (train.py:1024), recognised here by its `TVLoss_weight` attribute and evaluated -- value and gradient of all
+    six tensors -- by ONE streaming kernel (row f3).  Any other callable is applied tensor by tensor as the reference does."""
+    if hasattr(reg, "TVLoss_weight"):
+        from dynrf_b200 import extras as _ex
+
+        return _ex.tv_loss_vm(float(reg.TVLoss_weight), list(planes), list(lines))
     total = 0
     for p, l in zip(planes, lines):
         total = total + reg(p) * 1e-2 + reg(l) * 1e-3
@@ -58,7 +57,11 @@ class _VMMixin:
         return _offdiag_mean_abs(self.density_line) + _offdiag_mean_abs(self.app_line)
 
     def density_L1(self):
-        return self.feature2density(_dense_vm(self.density_plane, self.density_line)).abs().mean()
+        """reference models/tensoRF.py:80-98 / 378-396 materialises the dense C x Gy x Gx x Gz product (1.7 GB at 300^3);
+        here one kernel streams the tables and returns value + gradient (row f3)."""
+        from dynrf_b200 import extras as _ex
+
+        return _ex.dense_l1(self, list(self.density_plane), list(self.density_line))
 
     def TV_loss_density(self, reg):
         return _tv(reg, self.density_plane, self.density_line)
@@ -139,7 +142,9 @@ class TensorVMSplit_TimeEmbedding(_VMMixin, TensorBase):
         return [{"params": p, "lr": lr} for p, lr in groups]
 
     def blending_L1(self):
-        return self.feature2density(_dense_vm(self.blending_plane, self.blending_line)).abs().mean()
+        from dynrf_b200 import extras as _ex
+
+        return _ex.dense_l1(self, list(self.blending_plane), list(self.blending_line))
 
     def TV_loss_blending(self, reg):
         return _tv(reg, self.blending_plane, self.blending_line)

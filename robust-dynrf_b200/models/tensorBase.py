@@ -236,7 +236,11 @@ class TensorBase(nn.Module):
         return xyz, zvec[None], valid
 
     def sample_ray(self, rays_o, rays_d, is_train=True, N_samples=-1):
-        raise NotImplementedError("sample_ray (aabb marching) is unused by every shipped config (ray_type is ndc|contract)")
+        """aabb-entry + fixed-step marching (reference models/tensorBase.py:501-522; unused by the shipped configs).
+        -> rays_pts [N,S,3], interpx [N,S], ~mask_outbbox [N,S]."""
+        from dynrf_b200 import extras as _ex
+
+        return _ex.sample_ray(self, rays_o, rays_d, is_train, N_samples if N_samples > 0 else self.nSamples)
 
     # ------------------------------------------------------------------ a10: the field forward
     def forward(self, rays_chunk, ts_chunk, timeembeddings_chunk, xyz_sampled, z_vals, ray_valid, white_bg=True,

@@ -64,3 +64,90 @@ def render_rays(tensorf_static, tensorf, rays, ts, N_samples, ray_type="ndc"):
     fd = tensorf(rays, ts, None, xyz, z_vals, valid, is_train=False, ray_type=ray_type, N_samples=N_samples)
     out = raw2outputs(fs[6], fs[7], fd[6], fd[7], fd[9], fd[2], fd[8], rays, False, ray_type)
     return out, fs, fd
+
+
+# ----------------------------------------------------------------------------- f2: induced flow (renderer.py:1266-1392)
+
+
+def NDC2world(pts, H, W, f):
+    """reference renderer.py:1266-1274."""
+    pts_z = 2 / (torch.clamp(pts[..., 2:], min=-1.0, max=1 - 1e-6) - 1)
+    pts_x = -pts[..., 0:1] * pts_z * W / 2 / f
+    pts_y = -pts[..., 1:2] * pts_z * H / 2 / f
+    return torch.cat([pts_x, pts_y, pts_z], -1)
+
+
+def world2NDC(pts_world, H, W, f):
+    """reference renderer.py:1277-1283."""
+    o0 = -1.0 / (W / (2.0 * f)) * pts_world[..., 0:1] / pts_world[..., 2:]
+    o1 = -1.0 / (H / (2.0 * f)) * pts_world[..., 1:2] / pts_world[..., 2:]
+    o2 = 1.0 + 2.0 * 1 / pts_world[..., 2:]
+    return torch.cat([o0, o1, o2], -1)
+
+
+def contract2world(pts_contract):
+    """reference renderer.py:1286-1298 (functional form of its in-place masked update)."""
+    nrm = pts_contract.abs().amax(-1, keepdim=True)
+    return torch.where(nrm > 1.0, pts_contract / nrm * (-1 / (nrm - 2)), pts_contract)
+
+
+def _project(H, W, f, c2w, pts_map, ray_type):
+    """per-RAY tail of render_3d_point (renderer.py:1353-1376): [N,3] tensors only -- a few tiny torch ops whose autograd also
+    carries the pose / focal gradients of the static pose passes (train.py:1897-1933)."""
+    w2c = c2w[:, :3, :3].transpose(1, 2)
+    world = NDC2world(pts_map, H, W, f) if ray_type == "ndc" else contract2world(pts_map)
+    world = world - c2w[..., 3]
+    cam = torch.sum(world[..., None, :] * w2c[:, :3, :3], -1)
+    plane = torch.cat([cam[..., 0:1] / (-cam[..., 2:]) * f + W * 0.5, -cam[..., 1:2] / (-cam[..., 2:]) * f + H * 0.5], -1)
+    return plane, world2NDC(cam, H, W, f)
+
+
+def render_single_3d_point(H, W, f, c2w, pt_NDC):
+    """reference renderer.py:1301-1327."""
+    plane, cam_ndc = _project(H, W, f, c2w, pt_NDC, "ndc")
+    return plane, (cam_ndc[:, 2:] + 1.0) / 2.0
+
+
+def render_3d_point(H, W, f, c2w, weights, pts, rays, ray_type="ndc", scene_flow=None, clamp=None):
+    """reference renderer.py:1330-1376.  The per-SAMPLE part -- sum_s w * pts and sum_s w over [N,S] / [N,S,3] -- is one
+    kernel (forward and backward, dynrf_weighted_point_*); `scene_flow` / `clamp` (extensions, default off) fold the caller's
+    `pts_ref + scene_flow` and the contract-mode clamp (train.py:1371-1378) into that kernel."""
+    from dynrf_b200 import extras as _ex
+
+    pm, acc = _ex.weighted_point(weights, pts, scene_flow, clamp)
+    acc = acc[:, None]
+    if ray_type == "ndc":
+        pts_map = pm + (1.0 - acc) * (rays[:, :3] + rays[:, 3:])
+    elif ray_type == "contract":
+        far_pts = rays[:, :3] + rays[:, 3:] * 256.0
+        nrm = far_pts.abs().amax(-1, keepdim=True)
+        far_pts = torch.where(nrm > 1.0, (2 - 1 / nrm) * (far_pts / nrm), far_pts)
+        pts_map = pm + (1.0 - acc) * far_pts
+    else:
+        pts_map = pm
+    plane, cam_ndc = _project(H, W, f, c2w, pts_map, ray_type)
+    return plane, cam_ndc[:, 2:]
+
+
+def induce_flow_single(H, W, focal, pose_neighbor, pts_3d_neighbor, pts_2d):
+    """reference renderer.py:1379-1386."""
+    pts_2d_neighbor, _ = render_single_3d_point(H, W, focal, pose_neighbor, pts_3d_neighbor)
+    return pts_2d_neighbor - pts_2d
+
+
+def induce_flow(H, W, focal, pose_neighbor, weights, pts_3d_neighbor, pts_2d, rays, ray_type="ndc", scene_flow=None, clamp=None):
+    """reference renderer.py:1380-1392 -> (induced_flow [N,2], induced_disp [N,1])."""
+    pts_2d_neighbor, induced_disp = render_3d_point(H, W, focal, pose_neighbor, weights, pts_3d_neighbor, rays, ray_type,
+                                                    scene_flow=scene_flow, clamp=clamp)
+    return pts_2d_neighbor - pts_2d, induced_disp
+
+
+# ----------------------------------------------------------------------------- f1: fused ray generation
+
+
+def generate_rays(ray_idx, poses_refine9, focal_refine, H, W, ray_type="ndc", near=1.0, uv=None, view_ids=None, poses_mtx=None):
+    """train.py:1062-1077 as ONE kernel (+ its backward): ids2pixel -> get_ray_directions_lean -> get_rays_lean ->
+    ndc_rays_blender2 (NDC scenes), differentiable w.r.t. the 9-D poses and the focal length.  -> rays_train [B,6]."""
+    from dynrf_b200 import extras as _ex
+
+    return _ex.generate_rays(ray_idx, poses_refine9, focal_refine, H, W, ray_type, near, uv=uv, view_ids=view_ids, poses_mtx=poses_mtx)

@@ -101,14 +101,39 @@ def test_fullsize_tensor_core_vs_simt(cfg):
         assert bool(((o1[i] - o0[i]).abs() <= bound).all())
 
 
+CFG4 = dict(grid=[706, 786, 471], n=4096, s=256, ray_type="ndc", static_mode="MLP_Fea")
+
+
 @gpu
-def test_fullsize_subsample_against_oracle():
-    """512 of cfg 2's 4096 rays (every 8th) through the CPU oracle at the full 331x368x220 grid."""
-    case, models = _build(CFG2, seed=13)
-    sub = dict(case, rays=case["rays"][::8].contiguous(), ts=case["ts"][::8].contiguous())
+@pytest.mark.parametrize("cfg,stride", [(CFG2, 8), (CFG3, 16), (CFG4, 32)],
+                         ids=["cfg2_ndc_300cubed", "cfg3_contract_256cubed", "cfg4_ndc_640cubed"])
+def test_fullsize_subsample_against_oracle(cfg, stride):
+    """Every `stride`-th ray of the full batch through the CPU ORACLE at the configuration's full grid:
+    cfg 2 -- 512 NDC rays at [331,368,220]; cfg 3 -- 256 contracted rays x 192 samples at 256^3 (static head
+    MLP_Fea_TimeEmbedding); cfg 4 -- 128 NDC rays at [706,786,471] ("640^3", 421 MB of parameters)."""
+    case, models = _build(cfg, seed=13)
+    sub = dict(case, rays=case["rays"][::stride].contiguous(), ts=case["ts"][::stride].contiguous())
     ref = H.oracle_pass(sub)
     got = H.native_pass(sub, DEV, models=models)
-    print(H.compare_pass(ref, got))
+    print(H.compare_pass(ref, got, check=cfg["ray_type"] == "ndc"))
+    if cfg["ray_type"] != "ndc":
+        # contracted rays: dists reach several hundred on the outer samples, so alpha = 1 - exp(-sigma * dists) amplifies a
+        # 1e-6 sigma difference beyond the 1e-5 budget there; check alpha where the map is well conditioned and sigma everywhere
+        rep = H.compare_pass(ref, got, check=False)
+        assert rep["valid_mismatch"] == 0 and rep["xyz"] <= 1e-5 and rep["z"] <= 1e-4
+        for key in ("fs", "fd"):
+            r, g = ref[key], got[key]
+            assert float(((r[7] - g[7]).abs() / r[7].abs().clamp_min(1.0)).max()) <= 2e-5
+            ok = r[9] <= 4.0
+            a_r, a_g = 1 - torch.exp(-r[7] * r[9]), 1 - torch.exp(-g[7] * g[9])
+            assert float((a_r - a_g)[ok].abs().max()) <= H.TOL_ALPHA
+            assert float((r[4] - g[4]).abs().max()) <= 5e-5
+        assert rep["d_blending"] <= 2e-5 and rep["d_xyz_prime"] <= 2e-5
+        flips = rep["s_mask_flips"] + rep["d_mask_flips"]
+        for k in ("rgb_full", "rgb_s", "rgb_d"):
+            assert rep[f"o_{k}_rel"] <= H.TOL_RGB_REL + 1e-3 * (flips > 0), (k, rep)
+        for k in ("acc_full", "acc_s", "w_full", "w_s", "dyn"):
+            assert rep[f"o_{k}"] <= 1e-4, (k, rep)
 
 
 @gpu

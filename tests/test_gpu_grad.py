@@ -14,15 +14,40 @@ def _rel(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
 
 
-def _grad_ok(a, b, loose=3e-2, l2=5e-3):
-    """Agreement robust to ReLU-kink flips: a hidden unit whose pre-activation is ~1e-7 can land on the other side
-    of 0 on the GPU; that moves the unit's gradient row -- and, more weakly, everything upstream of it -- by one
-    sample's contribution (observed: 4e-3 of max on one row, everything else <= 4e-5).  Criterion: max-norm error
-    <= 3e-2 of max|ref| and L2 error <= 5e-3 of ||ref||; a wrong or missing term fails both by orders of magnitude."""
+def _grad_ok(a, b, loose=1e-3, l2=2e-3, kink_rows=2, kink_loose=3e-2):
+    """Tight gate with an EXPLICIT ReLU-kink exception.
+
+    Observed on B200 (smoke, round 1): worst relative-L2 error of any parameter gradient 2.4e-4, max-norm <= 4e-5 of max|ref|
+    -- except that a hidden unit whose pre-activation is ~1e-7 can land on the other side of 0 than on the CPU, which moves ONE
+    row (that unit's incoming weights / bias entry) or ONE column (its outgoing weights) of a weight gradient by one sample's
+    contribution (observed 4e-3 of max).  Gate: max-norm <= 1e-3 of max|ref| and L2 <= 2e-3 of ||ref||.  If that fails, up to
+    `kink_rows` rows and columns (2-D gradients) or entries (1-D) with the largest error may be set aside, provided each stays
+    within `kink_loose`; everything else must still pass the tight gate.  A wrong or missing term fails by orders of magnitude.
+    Returns (ok, max-norm error, relative L2 error)."""
     scale = float(b.abs().max()) + 1e-12
     err = (a - b).abs() / scale
+    emax = float(err.max())
     rel2 = float((a - b).norm() / (b.norm() + 1e-12))
-    return float(err.max()) <= loose and rel2 <= l2, float(err.max()), rel2
+    if emax <= loose and rel2 <= l2:
+        return True, emax, rel2
+    if emax > kink_loose or a.dim() > 2 or a.dim() == 0:
+        return False, emax, rel2
+    keep = torch.ones_like(err, dtype=torch.bool)
+    if a.dim() == 2:
+        for dim in (1, 0):                                  # worst rows, then worst columns
+            worst = err.amax(dim=dim)
+            idx = torch.topk(worst, min(kink_rows, worst.numel())).indices
+            idx = idx[worst[idx] > loose]
+            if dim == 1:
+                keep[idx, :] = False
+            else:
+                keep[:, idx] = False
+    else:
+        idx = torch.topk(err, min(kink_rows, err.numel())).indices
+        keep[idx[err[idx] > loose]] = False
+    d = (a - b) * keep
+    ok = float((d.abs() / scale).max()) <= loose and float(d.norm() / ((b * keep).norm() + 1e-12)) <= l2
+    return ok, emax, rel2
 
 
 def _loss_weights(shapes, seed):
@@ -204,6 +229,13 @@ def test_reference_golden_gradients(golden_case):
             want = float(g.raw[key])
             if abs(got - want) > 2e-3 * max(want, 1e-6):
                 bad[f"{tag}:{name}"] = (got, want)
+            # element-wise: the first 256 entries (NCHW-flattened order) of the gradient the reference's autograd produced
+            head = g.t(f"g_{tag}/{name}/head")
+            mine = p.grad.detach().cpu().contiguous().reshape(-1)[: head.numel()]
+            scale = max(float(head.abs().max()), 1e-3 * want / max(p.numel(), 1), 1e-12)
+            e = float((mine - head).abs().max()) / scale
+            if e > 5e-3:
+                bad[f"{tag}:{name}:head"] = e
     assert not bad, bad
 
 
@@ -233,5 +265,61 @@ def test_interleaved_forwards_keep_their_own_saved_state():
     alone, mixed = run(False), run(True)
     assert alone.keys() == mixed.keys()
     for k in alone:
-        ok, emax, e2 = _grad_ok(mixed[k].cpu(), alone[k].cpu(), loose=1e-3, l2=1e-4)
+        ok, emax, e2 = _grad_ok(mixed[k].cpu(), alone[k].cpu(), loose=1e-3, l2=1e-4, kink_rows=0)
         assert ok, (k, emax, e2)
+
+
+@gpu
+def test_parameter_gradients_cfg3_contract_256cubed():
+    """cfg 3 (DAVIS shape): contracted rays, 256^3 grid, S = 192, static head MLP_Fea_TimeEmbedding; 256 rays so that the
+    oracle's autograd finishes in seconds."""
+    test_parameter_gradients("contract", "MLP_Fea_TimeEmbedding", [256, 256, 256], 256, 192)
+
+
+@gpu
+def test_dynamic_xyz_gradient_request_raises():
+    """Nothing silently detaches: asking the dynamic field for d/d(xyz_sampled) must fail loudly."""
+    import renderer as R
+
+    case = H.build_pair([20, 22, 18], 32, 24, seed=5)
+    static, dyn = H.native_models(case, DEV)
+    rays = case["rays"].to(DEV).requires_grad_(True)
+    ts = case["ts"].to(DEV)
+    xyz, z, valid = R.sampleXYZ(dyn, rays, 24, "ndc", False)
+    assert xyz.requires_grad
+    fd = dyn(rays, ts, None, xyz, z, valid, ray_type="ndc")
+    with pytest.raises(NotImplementedError):
+        fd[7].sum().backward()
+    # the documented way: detached positions for the dynamic field, the static field carries d/dxyz
+    fd = dyn(rays.detach(), ts, None, xyz.detach(), z, valid, ray_type="ndc")
+    fs = static(rays, ts, None, xyz, z, valid, ray_type="ndc")
+    (fd[7].sum() + fs[7].sum() + fs[6].sum()).backward()
+    assert rays.grad is not None and bool(torch.isfinite(rays.grad).all())
+
+
+@gpu
+def test_tc_pack_rejects_unsupported_hyperparameters():
+    """the tensor-core packs are compiled for the shipped shapes; anything else raises instead of mis-reading weights."""
+    import models.tensoRF as T
+    import renderer as R
+
+    dev = torch.device(DEV)
+    aabb = torch.tensor(H.NDC_AABB, device=dev)
+    kw = dict(H.COMMON, near_far=[0.0, 1.0])
+    kw["featureC"] = 64
+    m = T.TensorVMSplit(aabb, [16, 16, 16], 12, dev, shadingMode="MLP_Fea", fea_pe=2, **kw)
+    g = torch.Generator().manual_seed(0)
+    rays, ts = H.synth_rays(16, "ndc", g)
+    rays, ts = rays.to(dev), ts.to(dev)
+    with torch.no_grad():
+        xyz, z, valid = R.sampleXYZ(m, rays, 16, "ndc", False)
+        with pytest.raises(NotImplementedError):
+            m(rays, ts, None, xyz, z, valid, ray_type="ndc")
+    kw = dict(H.COMMON, near_far=[0.0, 1.0])
+    m2 = T.TensorVMSplit(aabb, [16, 16, 16], 12, dev, shadingMode="MLP_Fea", fea_pe=6, **kw)   # class-default fea_pe
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        m2(rays, ts, None, xyz, z, valid, ray_type="ndc")
+    with pytest.raises(ValueError):
+        R.raw2outputs(torch.zeros(4, 8, 3, device=dev), torch.zeros(4, 8, device=dev), torch.zeros(4, 8, 3, device=dev),
+                      torch.zeros(4, 8, device=dev), torch.zeros(4, 8, device=dev), torch.zeros(4, 8, device=dev),
+                      torch.zeros(4, 8, device=dev), torch.zeros(4, 7, device=dev))

@@ -1,0 +1,169 @@
+"""K1 (k_static_sigma_weight, the north-star kernel: static density lookup + sigma->alpha + transmittance scan + weights)
+at the 300^3 and 640^3 grids, train-order (random pixels over all frames, train.py:88-93) and render-order (row-major pixels
+of one frame, renderer.py:1055) rays, both kernel variants (GEN=1: samples generated in-kernel; GEN=0: materialised inputs).
+
+    python tools/k1_table.py time  > gpurun_out/k1_time.json        # CUDA events, L2 flushed between launches
+    ncu --set full --clock-control none -k regex:k_static_sigma_weight -o gpurun_out/k1 python tools/k1_table.py ncu
+    python tools/k1_table.py merge gpurun_out/k1_time.json gpurun_out/k1.ncu-rep > profiles/r02_k1_table.json
+
+Algorithmic bytes per sample: 588 (GEN=1) / 605 (GEN=0).  Rays come from the ray generator the reference uses
+(identity poses, 1920x1080, focal 1000 -> NDC), restated in dynrf_b200 (f1); no oracle code is used here."""
+import csv
+import io
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "robust-dynrf_b200"))
+
+GRIDS = {"300^3": [331, 368, 220], "640^3": [706, 786, 471]}
+N, S = 4096, 256
+H_IMG, W_IMG, FRAMES, FOCAL = 1080, 1920, 24, 1000.0
+
+
+def ndc_rays(ids, dev):
+    """pixel ids -> NDC rays for identity camera poses (dataLoader/ray_utils.py:53-69, 115-140 with c2w = I, near = 1)."""
+    import torch
+
+    col, row = (ids % W_IMG).float() + 0.5, ((ids // W_IMG) % H_IMG).float() + 0.5
+    dx, dy, dz = (col - W_IMG / 2) / FOCAL, -(row - H_IMG / 2) / FOCAL, -torch.ones_like(col)
+    # origin 0 shifted to the near plane: o = t d with t = -1/dz = 1 -> o = (dx, dy, -1)
+    ox, oy, oz = dx, dy, dz
+    o0, o1, o2 = -1.0 / (W_IMG / (2 * FOCAL)) * ox / oz, -1.0 / (H_IMG / (2 * FOCAL)) * oy / oz, 1.0 + 2.0 / oz
+    d0 = -1.0 / (W_IMG / (2 * FOCAL)) * (dx / dz - ox / oz)
+    d1 = -1.0 / (H_IMG / (2 * FOCAL)) * (dy / dz - oy / oz)
+    d2 = -2.0 / oz
+    return torch.stack((o0, o1, o2, d0, d1, d2), -1).to(dev)
+
+
+def cases(dev):
+    import torch
+    import models.tensoRF as T
+    from dynrf_b200 import ops
+
+    g = torch.Generator().manual_seed(7)
+    orders = {"train": torch.randint(0, FRAMES * H_IMG * W_IMG, (N,), generator=g),
+              "render": torch.arange(N) + 500 * W_IMG}
+    aabb = torch.tensor([[-1.5, -1.67, -1.0], [1.5, 1.67, 1.0]], device=dev)
+    kw = dict(density_n_comp=[16, 4, 4], appearance_n_comp=[48, 12, 12], app_dim=27, alphaMask_thres=1e-4, density_shift=-10,
+              distance_scale=25, pos_pe=6, view_pe=0, featureC=128, step_ratio=2.0, fea2denseAct="relu", near_far=[0.0, 1.0])
+    for gname, grid in GRIDS.items():
+        torch.manual_seed(1)
+        m = T.TensorVMSplit(aabb, grid, 12, dev, shadingMode="MLP_Fea", fea_pe=2, **kw)
+        cfg = m.native_cfg("ndc")
+        zvec = ops.make_zvec(cfg, S, "ndc", False, dev)
+        for oname, ids in orders.items():
+            rays = ndc_rays(ids, dev)
+            xyz, z, valid = ops.sample_points(cfg, rays, zvec)
+            for gen in (1, 0):
+                def run(m=m, rays=rays, xyz=xyz, z=z, valid=valid, gen=gen, zvec=zvec):
+                    if gen:
+                        return ops.static_forward_raw(m, rays, None, None, None, "ndc", zvec=zvec)
+                    return ops.static_forward_raw(m, rays, xyz, z, valid, "ndc")
+                yield dict(grid=gname, order=oname, gen=gen), run
+        del m
+        torch.cuda.empty_cache()
+
+
+def main():
+    mode = sys.argv[1]
+    if mode == "merge":
+        return merge(sys.argv[2], sys.argv[3])
+    import torch
+
+    dev = torch.device("cuda", 0)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    rows = []
+    for meta, run in cases(dev):
+        run()
+        torch.cuda.synchronize()
+        if mode == "ncu":
+            flush.fill_(1)          # cold L2, like the timed launches
+            run()
+            torch.cuda.synchronize()
+            rows.append(meta)
+            continue
+        ts = []
+        for i in range(20):
+            flush.fill_(i & 0xFF)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = run()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        warm = []
+        for i in range(20):      # L2-warm: back-to-back launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = run()
+            e1.record()
+            torch.cuda.synchronize()
+            warm.append(e0.elapsed_time(e1))
+        ts.sort()
+        warm.sort()
+        active = int(r["cnt"].item())
+        rows.append(dict(meta, ms_cold_l2=sum(ts) / len(ts), ms_cold_l2_median=ts[len(ts) // 2], ms_warm_l2=sum(warm) / len(warm),
+                         active_fraction=active / (N * S)))
+    print(json.dumps({"n_rays": N, "n_samples": S, "rows": rows}))
+
+
+METRICS = {"dram_read": "dram__bytes_read.sum", "dram_write": "dram__bytes_write.sum", "lts_bytes": "lts__t_bytes.sum",
+           "l1tex_bytes": "l1tex__t_bytes.sum", "ns": "gpu__time_duration.sum",
+           "dram_pct": "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts_pct": "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+           "l1tex_pct": "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct": "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+           "issue_pct": "sm__inst_issued.avg.pct_of_peak_sustained_active", "lsu_wavefronts": "l1tex__data_pipe_lsu_wavefronts.sum",
+           "warps_active_pct": "sm__warps_active.avg.pct_of_peak_sustained_active"}
+
+
+def ncu_rows(rep, kernel_regex=None):
+    """-> list of per-launch dicts {kernel, metric: value} from an .ncu-rep (raw page)."""
+    cmd = ["ncu", "-i", rep, "--page", "raw", "--csv"]
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
+    rd = list(csv.reader(io.StringIO(out)))
+    hdr = rd[0]
+    res = []
+    for r in rd[2:]:
+        if len(r) != len(hdr):
+            continue
+        d = dict(zip(hdr, r))
+        row = {"kernel": d.get("Kernel Name", "")}
+        for k, mname in METRICS.items():
+            v = d.get(mname)
+            try:
+                row[k] = float(v.replace(",", "")) if v not in (None, "") else None
+            except ValueError:
+                row[k] = None
+        res.append(row)
+    return res
+
+
+def merge(time_json, rep):
+    t = json.load(open(time_json))
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+    launches = [r for r in ncu_rows(rep) if "k_static_sigma_weight" in r["kernel"]]
+    # the ncu mode launches every case twice (warm-up, then the L2-cold launch): take the second of each pair
+    cold = launches[1::2]
+    P = t["n_rays"] * t["n_samples"]
+    out = []
+    for row, m in zip(t["rows"], cold):
+        alg = P * (588 if row["gen"] else 605)
+        ms = row["ms_cold_l2"]
+        dram = (m["dram_read"] or 0) + (m["dram_write"] or 0)
+        out.append(dict(row, algorithmic_bytes=alg, algorithmic_gbs=alg / ms / 1e6, algorithmic_frac_of_hbm_peak=alg / ms / 1e6 / peaks["hbm_gbs"],
+                        dram_bytes=dram, dram_gbs=dram / ms / 1e6, dram_frac_of_hbm_peak=dram / ms / 1e6 / peaks["hbm_gbs"],
+                        lts_bytes=m["lts_bytes"], l1tex_bytes=m["l1tex_bytes"], ncu_ms=(m["ns"] or 0) / 1e6,
+                        ncu_pct_of_peak=dict(dram=m["dram_pct"], l2=m["lts_pct"], l1tex=m["l1tex_pct"], sm=m["sm_pct"], issue=m["issue_pct"],
+                                             warps_active=m["warps_active_pct"]), lsu_wavefronts=m["lsu_wavefronts"]))
+    print(json.dumps({"source": f"tools/k1_table.py (CUDA-event times, L2 flushed) + ncu --set full ({os.path.basename(rep)}), final build",
+                      "hbm_peak_gbs": peaks["hbm_gbs"], "n_rays": t["n_rays"], "n_samples": t["n_samples"],
+                      "note": "algorithmic_* counts every tap as moved (SURVEY 8d) and is an effective-bandwidth figure; dram_* is what DRAM "
+                              "delivered (ncu), ncu_pct_of_peak is each unit's utilisation by ncu's own peaks: the kernel is bound by the unit "
+                              "with the largest percentage, not by HBM.", "rows": out}, indent=1))
+
+
+if __name__ == "__main__":
+    main()
