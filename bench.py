@@ -320,7 +320,8 @@ def main():
         BX.run_train9(args, w, rank, world, dev, dist, ClockSampler, config_dict, METRIC)
         return
 
-    from tests import helpers as H
+    sys.path.insert(0, os.path.join(ROOT, "robust-dynrf_b200"))
+    from dynrf_b200 import synth as SY      # oracle-free workload construction
     from dynrf_b200 import lib as L
     from dynrf_b200 import train_step as TS
 
@@ -330,10 +331,9 @@ def main():
     N_RAYS, N_SAMPLES, GRID, RT = w["n_rays"], w["n_samples"], w["grid"], w["ray_type"]
 
     # identical parameters on every rank (replicated), a different ray shard per rank
-    case = H.build_pair(GRID, N_RAYS, N_SAMPLES, ray_type=RT, static_mode=w["static_mode"], seed=1)
-    static, dyn = H.native_models(case, dev)
+    static, dyn = SY.make_models(GRID, RT, w["static_mode"], dev, seed=1)
     g = torch.Generator().manual_seed(1000 + rank)
-    rays_h, ts_h = H.synth_rays(N_RAYS, RT, g)
+    rays_h, ts_h = SY.synth_rays(N_RAYS, RT, g)
     target_h = torch.rand(N_RAYS, 3, generator=g)
     rays_pin, ts_pin, target_pin = rays_h.pin_memory(), ts_h.pin_memory(), target_h.pin_memory()
     rays_d, ts_d, target_d = rays_h.to(dev), ts_h.to(dev), target_h.to(dev)

@@ -369,6 +369,16 @@ int dynrf_tv_fused(int n, const float* const* x, float* const* g_or_null, const 
  *     if g != NULL the gradient of that SUM is accumulated into g (caller zeroes).  C must be [16,4,4]. */
 int dynrf_dense_l1(const dynrf_vm_t* vm, int act, float shift, double* sum_out, const dynrf_vm_grad_t* g_or_null, void* stream);
 
+
+/* ---- optimiser: one-launch Adam over the flat gradient buffer of the train step (torch.optim.Adam semantics, no weight
+ * decay / amsgrad; train.py:934, 2313-2325).  param_ptr [T]: device array of the parameters' storage pointers (uint64);
+ * offset [T+1] (int64): prefix of numel in the flat grad / m / v buffers; blk0 [T+1] (int32) with
+ * blk0[t+1] - blk0[t] = dynrf_adam_blocks(numel_t); lr [T]; step [2]: step[0] float update count (incremented by the call),
+ * step[1] uint32 scratch that the caller zero-initialises once. */
+int dynrf_adam_blocks(long long numel);
+int dynrf_adam_flat(const uint64_t* param_ptr, const int64_t* offset, const int32_t* blk0, int T, int total_blocks, const float* grad,
+                    float* m, float* v, float* step, const float* lr, float beta1, float beta2, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,13 +29,36 @@ def available() -> bool:
         return False
 
 
+class ZeroArena:
+    """One zero-filled buffer per backward call from which the many small accumulators (packed layer gradients, bias / last-layer
+    partials, weight-gradient GEMM outputs) are carved: one memset instead of ~40 fill launches."""
+
+    def __init__(self, device, floats: int = 1 << 20):
+        self.buf = torch.zeros(floats, device=device)
+        self.off = 0
+
+    def take(self, *shape) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        a = (n + 15) // 16 * 16        # keep every carve 64-byte aligned (vector reductions need 16)
+        if self.off + a > self.buf.numel():
+            return torch.zeros(*shape, device=self.buf.device)
+        t = self.buf[self.off:self.off + n].view(*shape)
+        self.off += a
+        return t
+
+
 class GradLayer:
     """Packed gradient buffers of one nn.Linear."""
 
-    def __init__(self, pl: ops.PackedLayer):
+    def __init__(self, pl: ops.PackedLayer, arena: "ZeroArena" = None):
         self.pl = pl
-        self.dwt = torch.zeros(pl.Kpad * pl.Npad, device=pl.wt.device)
-        self.db = torch.zeros(pl.Npad, device=pl.wt.device)
+        if arena is not None:
+            self.dwt, self.db = arena.take(pl.Kpad * pl.Npad), arena.take(pl.Npad)
+        else:
+            self.dwt = torch.zeros(pl.Kpad * pl.Npad, device=pl.wt.device)
+            self.db = torch.zeros(pl.Npad, device=pl.wt.device)
         self.struct = L.LayerGradT(self.dwt.data_ptr(), self.db.data_ptr())
 
     def unpack(self):
@@ -60,10 +83,20 @@ def pack_bwd(pl: ops.PackedLayer, k0: int, k1: int, nrows: int) -> torch.Tensor:
     return wb
 
 
+# When set (the train step sets it: every p.grad is a live view of the flat gradient buffer), the plane / line gradients -- 93 MB
+# at cfg 2 -- are accumulated by the scatter kernels STRAIGHT into p.grad and the Functions return None for those inputs,
+# instead of filling 30 temporaries with zeros and letting AccumulateGrad add them (the kernels add with atomics either way).
+DIRECT_PLANE_GRADS = [False]
+
+
 def _vm_grads(planes, lines):
+    """-> (plane grads, line grads, dynrf_vm_grad_t, returned-to-autograd list)."""
+    if DIRECT_PLANE_GRADS[0] and all(p.grad is not None and p.grad.stride() == p.stride() for p in list(planes) + list(lines)):
+        gp, gl = [p.grad for p in planes], [p.grad for p in lines]
+        return gp, gl, ops.vm_grad_struct(gp, gl), [None] * (len(gp) + len(gl))
     gp = [ops.zeros_like_cl(p) for p in planes]
     gl = [ops.zeros_like_cl(p) for p in lines]
-    return gp, gl, ops.vm_grad_struct(gp, gl)
+    return gp, gl, ops.vm_grad_struct(gp, gl), gp + gl
 
 
 def _rays_grad_from(rays, z_vals, scale, gdists, gvd):
@@ -150,12 +183,13 @@ class StaticFieldFn(torch.autograd.Function):
         gvd = torch.zeros(n, 3, device=dev) if need_rays else None
         ly = m.packed_layers()
         pk = m._packed
-        gden_p, gden_l, gden = _vm_grads(m.density_plane, m.density_line)
-        gapp_p, gapp_l, gapp = _vm_grads(m.app_plane, m.app_line)
-        gl = {k: GradLayer(pk[k]) for k in ("basis", "h1", "h2", "h3")}
+        arena = ZeroArena(dev)
+        gden_p, gden_l, gden, ret_den = _vm_grads(m.density_plane, m.density_line)
+        gapp_p, gapp_l, gapp, ret_app = _vm_grads(m.app_plane, m.app_line)
+        gl = {k: GradLayer(pk[k], arena) for k in ("basis", "h1", "h2", "h3")}
         tc_head = None
         if grgb is not None and ops.USE_TC and st.get("featT") is not None:
-            tc_head = _head_bwd_tc(m, cfg, st, st["xyz"], None, _f32c(grgb), gl, gapp, gxyz, gvd, n, s)
+            tc_head = _head_bwd_tc(m, cfg, st, st["xyz"], None, _f32c(grgb), gl, gapp, gxyz, gvd, n, s, arena)
         elif grgb is not None:
             vapp = ops.vm_struct(m.app_plane, m.app_line)
             wb2 = pack_bwd(pk["h2"], 0, 128, 128)
@@ -177,7 +211,7 @@ class StaticFieldFn(torch.autograd.Function):
             g1w, g1b = gl["h1"].unpack()
             g2w, g2b = gl["h2"].unpack()
             g3w, g3b = gl["h3"].unpack()
-        pg = gden_p + gden_l + gapp_p + gapp_l + [gb, g1w, g1b, g2w, g2b, g3w, g3b]
+        pg = ret_den + ret_app + [gb, g1w, g1b, g2w, g2b, g3w, g3b]
         return (None, None, grays, gxyz, None, None, *pg)
 
 
@@ -228,13 +262,14 @@ class DynamicFieldFn(torch.autograd.Function):
         gxp = _f32c(gxyzp).clone() if gxyzp is not None else torch.zeros(n, s, 3, device=dev)
         ly = m.packed_layers()
         pk = m._packed
-        gl = {k: GradLayer(pk[k]) for k in _DYN_LAYER_ORDER}
-        gbl_p, gbl_l, gbl = _vm_grads(m.blending_plane, m.blending_line)
-        gden_p, gden_l, gden = _vm_grads(m.density_plane, m.density_line)
-        gapp_p, gapp_l, gapp = _vm_grads(m.app_plane, m.app_line)
+        arena = ZeroArena(dev)
+        gl = {k: GradLayer(pk[k], arena) for k in _DYN_LAYER_ORDER}
+        gbl_p, gbl_l, gbl, ret_bl = _vm_grads(m.blending_plane, m.blending_line)
+        gden_p, gden_l, gden, ret_den = _vm_grads(m.density_plane, m.density_line)
+        gapp_p, gapp_l, gapp, ret_app = _vm_grads(m.app_plane, m.app_line)
         tc_head = None
         if grgb is not None and ops.USE_TC and r.get("featT") is not None:
-            tc_head = _head_bwd_tc(m, cfg, r, r["xyz_prime"], r["tfeat"], _f32c(grgb), gl, gapp, gxp, None, n, s)
+            tc_head = _head_bwd_tc(m, cfg, r, r["xyz_prime"], r["tfeat"], _f32c(grgb), gl, gapp, gxp, None, n, s, arena)
         elif grgb is not None:
             vapp = ops.vm_struct(m.app_plane, m.app_line)
             wb2 = pack_bwd(pk["h2"], 0, 128, 128)
@@ -250,7 +285,7 @@ class DynamicFieldFn(torch.autograd.Function):
         vbl = ops.vm_struct(m.blending_plane, m.blending_line)
         tc_sb = None
         if ops.USE_TC:
-            tc_sb = _dyn_mlp_bwd_tc(m, cfg, r, vden, vbl, gden, gbl, gsig, _f32c(gblend) if gblend is not None else None, gxp, n, s)
+            tc_sb = _dyn_mlp_bwd_tc(m, cfg, r, vden, vbl, gden, gbl, gsig, _f32c(gblend) if gblend is not None else None, gxp, n, s, arena)
         for mode, vm, gvm, k1, k2, gout in ((0, vden, gden, "d1", "d2", gsig), (1, vbl, gbl, "b1", "b2", gblend)):
             if gout is None or tc_sb is not None:
                 continue
@@ -258,7 +293,7 @@ class DynamicFieldFn(torch.autograd.Function):
             L.check(lib.dynrf_dyn_mlp_bwd(C.byref(cfg), mode, C.byref(vm), C.byref(gvm), C.byref(ly[k1]), C.byref(ly[k2]), _p(wbf),
                                           _p(r["xyz"]), _p(r["xyz_prime"]), _p(r["valid"]), _p(r["tfeat"]), n, s, _p(_f32c(gout)),
                                           C.byref(gl[k1].struct), C.byref(gl[k2].struct), _p(gxp), _stream()), "dynrf_dyn_mlp_bwd")
-        gtout = torch.zeros(n, 32, device=dev)
+        gtout = arena.take(n, 32)
         wb4 = pack_bwd(pk["layer4"], 0, 64, 64)
         wb3t = pack_bwd(pk["layer3"], 63, 93, 64)
         L.check(lib.dynrf_warp_bwd(C.byref(cfg), _p(r["xyz"]), n, s, _p(r["tfeat"]), C.byref(ly["layer3"]), C.byref(ly["layer4"]),
@@ -269,7 +304,7 @@ class DynamicFieldFn(torch.autograd.Function):
                                          C.byref(gl["layer1"].struct), C.byref(gl["layer2"].struct), _stream()),
                 "dynrf_time_embed_bwd")
         grays = _rays_grad_from(r["rays"], r["z_vals"], float(m.distance_scale), gd, None) if ctx.needs_input_grad[2] else None
-        pg = gbl_p + gbl_l + gden_p + gden_l + gapp_p + gapp_l
+        pg = ret_bl + ret_den + ret_app
         for k in _DYN_LAYER_ORDER:
             if tc_head is not None and k in tc_head:
                 dw, db = tc_head[k]
@@ -331,7 +366,7 @@ def _wgrad(XT, K, DYT, N, ld, cnt, out, out_ld):
     L.check(L.load().dynrf_wgrad_gemm(_p(XT), ld, K, _p(DYT), ld, N, ld, _p(cnt), _p(out), out_ld, _stream()), "dynrf_wgrad_gemm")
 
 
-def _head_bwd_tc(m, cfg, r, coords, tfeat, grgb, gl, gapp, gcoord, gvd, n, s):
+def _head_bwd_tc(m, cfg, r, coords, tfeat, grgb, gl, gapp, gcoord, gvd, n, s, arena=None):
     """Tensor-core appearance-head backward: fused tile kernel (recompute + data gradients) -> wgrad GEMMs -> basis / lookups.
     r: forward record (rays, xyz, featT, ldf, idx, cnt); coords: lookup coordinates; gcoord: their gradient (+=) or None."""
     lib = L.load()
@@ -345,19 +380,20 @@ def _head_bwd_tc(m, cfg, r, coords, tfeat, grgb, gl, gapp, gcoord, gvd, n, s):
     xr = st.xrows
     l1 = m._layer_table()["h1"]
     k1 = l1.weight.shape[1]
-    small = torch.zeros(3 * 128 + 9 + 3 + 128, device=dev)    # gw3h [3][128] | gw3v [3][3] | gb3 [3] | gb2 [128]
+    arena = arena if arena is not None else ZeroArena(dev, 1 << 17)
+    small = arena.take(3 * 128 + 9 + 3 + 128)    # gw3h [3][128] | gw3v [3][3] | gb3 [3] | gb2 [128]
     gw3h, gw3v, gb3, gb2 = small[:384].view(3, 128), small[384:393].view(3, 3), small[393:396], small[396:524]
     L.check(lib.dynrf_head_bwd_tc(C.byref(cfg), st.dyn, _p(st.wq), _p(st.cst), _p(r["rays"]), _p(r["xyz"]), _p(tfeat), _p(r["featT"]),
                                   _p(grgb), _p(r["idx"]), _p(r["cnt"]), n, s, ld, _p(b["X1T"]), _p(b["H1T"]), _p(b["DH2T"]),
                                   _p(b["DH1T"]), _p(b["DFT"]), _p(gw3h), _p(gw3v), _p(gb3), _p(gb2), _p(gvd), _stream()),
             "dynrf_head_bwd_tc")
     cnt = r["cnt"]
-    dw1m = torch.zeros(128, xr, device=dev)
+    dw1m = arena.take(128, xr)
     _wgrad(b["X1T"], xr, b["DH1T"], 128, ld, cnt, dw1m, xr)
-    dw1 = torch.zeros(128, k1, device=dev)
+    dw1 = arena.take(128, k1)
     dw1[:, st.dst_cols] = dw1m[:, st.src_rows]
     db1 = dw1m[:, xr - 1].contiguous()
-    dw2 = torch.zeros(128, 128, device=dev)
+    dw2 = arena.take(128, 128)
     _wgrad(b["H1T"], 128, b["DH2T"], 128, ld, cnt, dw2, 128)
     k3 = m._layer_table()["h3"].weight.shape[1]
     dw3 = torch.cat((gw3h, gw3v), 1) if k3 == 131 else gw3h
@@ -408,7 +444,7 @@ class _SbBwdState:
         return b
 
 
-def _dyn_mlp_bwd_tc(m, cfg, r, vden, vbl, gden, gbl, gsig, gblend, gxp, n, s):
+def _dyn_mlp_bwd_tc(m, cfg, r, vden, vbl, gden, gbl, gsig, gblend, gxp, n, s, arena=None):
     """Tensor-core backward of the density + blending MLPs (a16 + a17): one fused tile kernel + one wgrad GEMM."""
     lib = L.load()
     st = m.__dict__.get("_sb_bwd_state")
@@ -423,13 +459,14 @@ def _dyn_mlp_bwd_tc(m, cfg, r, vden, vbl, gden, gbl, gsig, gblend, gxp, n, s):
         saved = None
     b = st.scratch(ld, dev, need_xt=saved is None)
     xt = saved["XT"] if saved is not None else b["XT"]
-    gsmall = torch.zeros(258, device=dev)      # gw2 (128) | gb1 (128) | gb2 (2)
+    arena = arena if arena is not None else ZeroArena(dev, 1 << 16)
+    gsmall = arena.take(258)      # gw2 (128) | gb1 (128) | gb2 (2)
     L.check(lib.dynrf_dyn_mlp_bwd_tc(C.byref(cfg), C.byref(vden), C.byref(vbl), C.byref(gden), C.byref(gbl), _p(st.wq), _p(st.cst),
                                      _p(r["xyz"]), _p(r["xyz_prime"]), _p(r["valid"]), _p(r["tfeat"]), _p(gsig), _p(gblend), n, s, ld,
                                      _p(xt), _p(saved["HT"]) if saved is not None else None, _p(b["DHT"]), _p(gxp), _p(gsmall),
                                      _p(gsmall[128:]), _p(gsmall[256:]), _stream()),
             "dynrf_dyn_mlp_bwd_tc")
-    dwf = torch.zeros(128, 224, device=dev)
+    dwf = arena.take(128, 224)
     L.check(lib.dynrf_wgrad_gemm(_p(xt), ld, 224, _p(b["DHT"]), ld, 128, P, None, _p(dwf), 224, _stream()), "dynrf_wgrad_gemm")
     dw_d = torch.empty(64, 152, device=dev)
     dw_b = torch.empty(64, 152, device=dev)
@@ -487,32 +524,22 @@ class CompositeFn(torch.autograd.Function):
 
 
 def _train_setup(step):
+    from . import optim
+
     static, dyn = step.static, step.dyn
     params = list(static.parameters()) + [p for n_, p in dyn.named_parameters() if not n_.startswith("scene_flow")]
     step.params = params
     # one flat gradient buffer; every p.grad is a view into it, so a data-parallel step all-reduces one tensor and the
     # buffer addresses are stable under CUDA-graph replay.  Views keep each parameter's own (channel-last) strides.
-    total = sum(p.numel() for p in params)
-    step.flat_grad = torch.zeros(total, device=params[0].device)
-    off = 0
-    for p in params:
-        k = p.numel()
-        p.grad = torch.as_strided(step.flat_grad, p.shape, p.stride(), off) if _dense(p) else step.flat_grad[off:off + k].view(p.shape)
-        off += k
-    step.opt = torch.optim.Adam(params, lr=1e-4, betas=(0.9, 0.99), capturable=True, foreach=True)
+    step.flat_grad = optim.alias_grads(params)
+    # one-launch Adam over the flat buffer (torch's foreach / capturable Adam is ~150 small launches on these 66 tensors)
+    step.opt = optim.FlatAdam(params, step.flat_grad, lr=1e-4, betas=(0.9, 0.99))
 
 
 def _dense(p):
-    """True if p's strides are a permutation of a dense layout over numel() elements (safe to alias with as_strided)."""
-    if p.is_contiguous():
-        return True
-    sz_st = sorted(((st, sz) for sz, st in zip(p.shape, p.stride()) if sz > 1))
-    exp = 1
-    for st, sz in sz_st:
-        if st != exp:
-            return False
-        exp *= sz
-    return True
+    from .optim import dense_storage
+
+    return dense_storage(p)
 
 
 def train_fwd_bwd(step, rays, ts, target):
@@ -523,6 +550,7 @@ def train_fwd_bwd(step, rays, ts, target):
     if getattr(step, "opt", None) is None:
         _train_setup(step)
     step.flat_grad.zero_()
+    DIRECT_PLANE_GRADS[0] = True      # every p.grad is a live, zeroed view of step.flat_grad for the whole backward below
     rays_s = rays
     if getattr(step, "rays_grad", False):
         # pose / focal optimisation (cfg 3/4): the rays carry requires_grad; as in the reference's passes 5-9 the gradient reaches
@@ -534,7 +562,10 @@ def train_fwd_bwd(step, rays, ts, target):
     fd = dyn(rays, ts, None, xyz.detach(), z, valid, is_train=True, ray_type=step.rt, N_samples=step.s)
     o = R.raw2outputs(fs[6], fs[7], fd[6], fd[7], fd[9], fd[2], fd[8], rays, False, step.rt)
     loss = ((o[0] - target) ** 2).mean() + ((o[4] - target) ** 2).mean() + ((o[8] - target) ** 2).mean()
-    loss.backward()
+    try:
+        loss.backward()
+    finally:
+        DIRECT_PLANE_GRADS[0] = False
     if rays_s is not rays:
         step.rays_grad_out = rays_s.grad
     out = torch.cat((o[0], o[1][:, None], o[2][:, None], o[4], o[5][:, None], o[6][:, None], o[8], o[9][:, None],

@@ -14,7 +14,7 @@ PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # robust
 CSRC = os.path.join(PKG_ROOT, "csrc")
 LIB_DIR = os.path.join(PKG_ROOT, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdynrf_b200.so")
-SOURCES = ["ray_kernels.cu", "field_kernels.cu", "backward_kernels.cu", "selftest.cu", "tc_kernels.cu", "wgrad_gemm.cu", "tc_bwd_kernels.cu", "tc_sb_bwd.cu", "tc_app_fwd.cu", "extras_kernels.cu"]
+SOURCES = ["ray_kernels.cu", "field_kernels.cu", "backward_kernels.cu", "selftest.cu", "tc_kernels.cu", "wgrad_gemm.cu", "tc_bwd_kernels.cu", "tc_sb_bwd.cu", "tc_app_fwd.cu", "extras_kernels.cu", "optim_kernels.cu"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -140,11 +140,13 @@ PROTOTYPES = {
     "dynrf_weighted_point_bwd": [_P, _P, _P, _I, _F, _F, _I, _I, _P, _P, _P, _P, _P],
     "dynrf_tv_fused": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "dynrf_dense_l1": [_vm, _I, _F, _P, _vg, _P],
+    "dynrf_adam_blocks": [C.c_longlong],
+    "dynrf_adam_flat": [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _F, _F, _F, _P],
     "dynrf_dyn_sigma_blend_fwd_tc": [_cfg, _vm, _vm, _ul, _ly, _ul, _ly, _P, _P, _P, _P, _I, _I, _P, _P, _P],
 }
 
 _lib = None
-_NO_LAUNCH = {"dynrf_abi_version", "dynrf_pad_k", "dynrf_pad_n", "dynrf_strerror", "dynrf_sb_umma_floats", "dynrf_head_bwd_wfloats", "dynrf_head_bwd_cst_floats", "dynrf_head_bwd_xrows", "dynrf_sb_bwd_wfloats", "dynrf_app_fwd_wfloats", "dynrf_app_fwd_cst_floats"}
+_NO_LAUNCH = {"dynrf_abi_version", "dynrf_pad_k", "dynrf_pad_n", "dynrf_strerror", "dynrf_sb_umma_floats", "dynrf_head_bwd_wfloats", "dynrf_head_bwd_cst_floats", "dynrf_head_bwd_xrows", "dynrf_sb_bwd_wfloats", "dynrf_app_fwd_wfloats", "dynrf_app_fwd_cst_floats", "dynrf_adam_blocks"}
 
 # every other entry point enqueues exactly one kernel of this library; bench.py reports the count
 launch_count = 0

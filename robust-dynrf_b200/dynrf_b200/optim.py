@@ -1,0 +1,74 @@
+"""FlatAdam: torch.optim.Adam semantics (no weight decay / amsgrad) as ONE kernel launch over a flat gradient buffer.
+
+The train step keeps every gradient in one flat fp32 buffer that each p.grad aliases with the parameter's own dense strides
+(channel-last planes included), so storage element i of a parameter pairs with flat_grad[offset + i].  Capturable by
+construction: the step counter lives on the device (train.py:934, 2313-2325 use torch.optim.Adam)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Sequence, Union
+
+import torch
+
+from . import lib as L
+from .ops import _p, _stream
+
+
+def dense_storage(p: torch.Tensor) -> bool:
+    """True if p's strides are a permutation of a dense layout over numel() elements."""
+    if p.is_contiguous():
+        return True
+    exp = 1
+    for st, sz in sorted(((st, sz) for sz, st in zip(p.shape, p.stride()) if sz > 1)):
+        if st != exp:
+            return False
+        exp *= sz
+    return True
+
+
+def alias_grads(params: Sequence[torch.nn.Parameter]) -> torch.Tensor:
+    """One flat zero buffer; every p.grad becomes a view of it with p's own strides.  -> the flat buffer."""
+    dev = params[0].device
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+    off = 0
+    for p in params:
+        if not dense_storage(p):
+            raise ValueError("FlatAdam needs densely stored parameters")
+        p.grad = torch.as_strided(flat, p.shape, p.stride(), off)
+        off += p.numel()
+    return flat
+
+
+class FlatAdam:
+    def __init__(self, params: Sequence[torch.nn.Parameter], flat_grad: torch.Tensor, lr: Union[float, Sequence[float]] = 1e-3,
+                 betas=(0.9, 0.999), eps: float = 1e-8):
+        lib = L.load()
+        self.params = list(params)
+        self.flat_grad = flat_grad
+        dev = flat_grad.device
+        T = len(self.params)
+        offs, blks = [0], [0]
+        for p in self.params:
+            if p.dtype != torch.float32 or not dense_storage(p) or p.storage_offset() != 0 and False:
+                raise ValueError("FlatAdam: fp32, densely stored parameters only")
+            offs.append(offs[-1] + p.numel())
+            blks.append(blks[-1] + lib.dynrf_adam_blocks(C.c_longlong(p.numel())))
+        assert offs[-1] == flat_grad.numel()
+        self.T, self.total_blocks = T, blks[-1]
+        self.ptrs = torch.tensor([p.data_ptr() for p in self.params], dtype=torch.int64, device=dev)   # re-read on rebuild()
+        self.offset = torch.tensor(offs, dtype=torch.int64, device=dev)
+        self.blk0 = torch.tensor(blks, dtype=torch.int32, device=dev)
+        lrs = [float(lr)] * T if not isinstance(lr, (list, tuple)) else [float(x) for x in lr]
+        self.lr = torch.tensor(lrs, dtype=torch.float32, device=dev)
+        self.m = torch.zeros_like(flat_grad)
+        self.v = torch.zeros_like(flat_grad)
+        self.state = torch.zeros(2, dtype=torch.float32, device=dev)     # [update count, kernel scratch]
+        self.betas, self.eps = betas, eps
+
+    def step(self):
+        L.check(L.load().dynrf_adam_flat(_p(self.ptrs), _p(self.offset), _p(self.blk0), self.T, self.total_blocks, _p(self.flat_grad),
+                                         _p(self.m), _p(self.v), _p(self.state), _p(self.lr), float(self.betas[0]), float(self.betas[1]),
+                                         float(self.eps), _stream()), "dynrf_adam_flat")
+
+    def zero_grad(self):
+        self.flat_grad.zero_()

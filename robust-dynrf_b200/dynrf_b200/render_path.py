@@ -68,9 +68,6 @@ class RenderDriver:
     @torch.no_grad()
     def render_frame(self, c2w: torch.Tensor, t: float, slot: int) -> torch.Tensor:
         """c2w [3,4] (device) -> device frame buffer [H*W,16] (slot 0/1)."""
-        from . import lib as L
-
-        n0 = L.launch_count
         n = self.H * self.W
         rays = extras._RayGenFn.apply(self.ids, c2w.reshape(1, 3, 4).contiguous(), self.focal_t, self.H, self.W, self.rt == "ndc", 1.0, None, None)
         ts = torch.full((self.chunk,), float(t), device=self.dev)
@@ -81,7 +78,8 @@ class RenderDriver:
         if self.tail:
             lo = self.n_full * self.chunk
             buf[lo:].copy_(self.step_tail(rays[lo:], ts[: self.tail], None, fused=True))
-        self.launches += (L.launch_count - n0)
+        # a graph replay launches the kernels its eager warm-up step counted (Step.launches_per_step); + 1 ray-generation kernel
+        self.launches += 1 + self.n_full * (self.step_full.launches_per_step or 0) + ((self.step_tail.launches_per_step or 0) if self.tail else 0)
         return buf
 
     def render(self, poses: np.ndarray, times: Optional[List[float]] = None, frames: Optional[List[int]] = None):

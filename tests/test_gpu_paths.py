@@ -1,0 +1,96 @@
+"""-m gpu: the cfg-4 nine-pass train step (dynrf_b200/train9.py) and the cfg-5 frame-sharded render driver
+(dynrf_b200/render_path.py) at small sizes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rodynrf_extras as X
+from tests import helpers as H
+
+gpu = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@gpu
+@pytest.mark.parametrize("graph", [False, True])
+def test_train9_step_runs_and_reaches_every_parameter(graph):
+    from dynrf_b200 import train9 as T9
+
+    case = H.build_pair([24, 28, 20], 8, 32, seed=4)
+    static, dyn = H.native_models(case, DEV)
+    step = T9.Train9(static, dyn, 32, "ndc", 27, 48, 5, focal=40.0, graph=graph, tv_weight=1e-3)
+    g = torch.Generator().manual_seed(0)
+    batch = T9.synth_batch(256, 27, 48, 5, g, torch.device(DEV))
+    before = {n: p.detach().clone() for n, p in list(static.named_parameters()) + list(dyn.named_parameters())}
+    p0, f0 = step.poses.detach().clone(), step.focal.detach().clone()
+    for _ in range(2):
+        out = step(batch)
+    torch.cuda.synchronize()
+    assert out.shape == (256, 5) and bool(torch.isfinite(out).all())
+    assert bool(torch.isfinite(step.flat_grad).all())
+    moved = {n: float((p.detach() - before[n]).abs().max()) for n, p in list(static.named_parameters()) + list(dyn.named_parameters())}
+    stuck = [n for n, v in moved.items() if v == 0.0]
+    assert not stuck, f"parameters that never received a gradient: {stuck}"
+    assert float((step.poses.detach() - p0).abs().max()) > 0 and float((step.focal.detach() - f0).abs().max()) > 0
+
+
+@gpu
+def test_render_driver_matches_whole_frame_render():
+    import renderer as R
+    from dynrf_b200 import render_path as RP
+
+    case = H.build_pair([24, 28, 20], 8, 40, seed=6)
+    static, dyn = H.native_models(case, DEV)
+    Himg, Wimg, focal = 30, 52, 45.0
+    poses = RP.change_view_time_poses(np.concatenate([np.eye(3), np.zeros((3, 1))], 1), max_trans=0.05, length=7)
+    drv = RP.RenderDriver(static, dyn, Himg, Wimg, focal, 40, "ndc", chunk=512, graph=True)
+    frames = drv.render(poses, frames=[0, 3, 6])
+    maps3 = frames[1][1].clone() if False else None
+    # re-render frame 3 alone (the pinned buffers are reused every second frame) and compare with one un-chunked pass
+    got = drv.render(poses, frames=[3])[0][1].clone()
+    ids = torch.arange(Himg * Wimg)
+    pose9 = torch.cat((torch.eye(3)[:2].reshape(1, 6), torch.zeros(1, 3)), -1)
+    c2w = torch.as_tensor(poses[3], dtype=torch.float32)
+    # oracle rays for this pose: the 9-D parametrisation cannot express an arbitrary c2w, so compare the kernel against the
+    # restated formula directly (identity rotation + translation is what change_view_time produces)
+    assert torch.allclose(c2w[:, :3], torch.eye(3), atol=1e-6)
+    pose9[0, 6:9] = c2w[:, 3]
+    rays_ref = X.generate_rays(ids, pose9, torch.tensor(focal), Himg, Wimg, "ndc")
+    rays = R.generate_rays(ids.to(DEV), None, torch.tensor([focal], device=DEV), Himg, Wimg, "ndc", poses_mtx=c2w[None].to(DEV))
+    torch.testing.assert_close(rays.cpu(), rays_ref, rtol=1e-5, atol=1e-6)
+    t = RP.frame_time(3, 7)
+    ts = torch.full((Himg * Wimg,), t, device=DEV)
+    out, _, _ = R.render_rays(static, dyn, rays, ts, 40, "ndc")
+    whole = torch.cat((out[0], out[1][:, None], out[2][:, None], out[4], out[5][:, None], out[6][:, None], out[8], out[9][:, None],
+                       out[10][:, None], out[12][:, None]), -1)
+    torch.cuda.synchronize()
+    assert torch.equal(got, whole.cpu()), "chunked graph replay differs from the un-chunked render"
+    assert len(frames) == 3 and frames[0][0] == 0 and frames[2][0] == 6
+    assert drv.launches > 0
+
+
+@gpu
+def test_flat_adam_matches_torch_adam():
+    """One-launch Adam over the flat gradient buffer == torch.optim.Adam (same hyper-parameters), incl. a channel-last plane."""
+    from dynrf_b200 import optim
+
+    g = torch.Generator().manual_seed(0)
+    shapes = [(1, 16, 37, 29), (1, 4, 11, 1), (128, 138), (128,), (3, 131), (5000,)]
+    ref = [torch.nn.Parameter(torch.randn(s, generator=g).to(DEV)) for s in shapes]
+    mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    with torch.no_grad():
+        mine[0].data = mine[0].data.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)    # channel-last storage
+    flat = optim.alias_grads(mine)
+    opt_ref = torch.optim.Adam(ref, lr=1e-3, betas=(0.9, 0.99))
+    opt = optim.FlatAdam(mine, flat, lr=1e-3, betas=(0.9, 0.99))
+    for it in range(7):
+        grads = [torch.randn(s, generator=g).to(DEV) * (10.0 ** (it % 3 - 1)) for s in shapes]
+        for p, q, gr in zip(ref, mine, grads):
+            p.grad = gr.clone()
+            q.grad.copy_(gr)
+        opt_ref.step()
+        opt.step()
+    torch.cuda.synchronize()
+    assert float(opt.state[0]) == 7.0
+    for p, q in zip(ref, mine):
+        torch.testing.assert_close(q.detach(), p.detach(), rtol=2e-6, atol=2e-7)
