@@ -321,7 +321,7 @@ def main():
         return
 
     sys.path.insert(0, os.path.join(ROOT, "robust-dynrf_b200"))
-    from dynrf_b200 import synth as SY      # oracle-free workload construction
+    from dynrf_b200 import synth as SY      # product-only workload construction
     from dynrf_b200 import lib as L
     from dynrf_b200 import train_step as TS
 

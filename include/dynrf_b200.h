@@ -332,10 +332,6 @@ int dynrf_dyn_mlp_bwd_tc(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density
 int dynrf_wgrad_gemm(const float* XT, int ldx, int K, const float* DYT, int ldy, int N, int Pmax, const int32_t* count_ptr,
                      float* dw, int dw_ld, void* stream);
 
-/* Self-test of the tcgen05 tile-GEMM building block: C[128][N] = A[128][K] x B[N][K]^T, N in {32,64,128},
- * passes = 1 (TF32) or 3 (split TF32, ~fp32 accuracy).  Used by tests/test_gpu_umma.py. */
-int dynrf_selftest_umma_gemm(const float* A, const float* B, int K, int N, int passes, float* C, void* stream);
-
 /* ---- rows next to the ray-march path -----------------------------------------------------------
  * a4: TensorBase.sample_ray (models/tensorBase.py:501-522): aabb entry distance + fixed-step marching.
  *     jitter: [N] uniforms (is_train) or NULL.  Outputs xyz [N][S][3], z_vals [N][S] (per ray), valid [N][S]. */

@@ -14,7 +14,7 @@ PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # robust
 CSRC = os.path.join(PKG_ROOT, "csrc")
 LIB_DIR = os.path.join(PKG_ROOT, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdynrf_b200.so")
-SOURCES = ["ray_kernels.cu", "field_kernels.cu", "backward_kernels.cu", "selftest.cu", "tc_kernels.cu", "wgrad_gemm.cu", "tc_bwd_kernels.cu", "tc_sb_bwd.cu", "tc_app_fwd.cu", "extras_kernels.cu", "optim_kernels.cu"]
+SOURCES = ["ray_kernels.cu", "field_kernels.cu", "backward_kernels.cu", "tc_kernels.cu", "wgrad_gemm.cu", "tc_bwd_kernels.cu", "tc_sb_bwd.cu", "tc_app_fwd.cu", "extras_kernels.cu", "optim_kernels.cu"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -126,7 +126,6 @@ PROTOTYPES = {
     "dynrf_dyn_mlp_bwd_tc": [_cfg, _vm, _vm, _vg, _vg, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "dynrf_basis_bwd": [_cfg, _I, _vm, _vg, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "dynrf_wgrad_gemm": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _I, _P],
-    "dynrf_selftest_umma_gemm": [_P, _P, _I, _I, _I, _P, _P],
     "dynrf_pack_linear_umma": [_P, _P, _I, _I, _P, _P, _P],
     "dynrf_sb_umma_floats": [],
     "dynrf_pack_sb_umma": [_P, _P, _P, _P],

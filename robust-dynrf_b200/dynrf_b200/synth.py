@@ -1,6 +1,6 @@
 """Synthetic workloads for bench.py's native arm and the tools: seeded rays with the value distributions the survey
 states and the two drop-in models at reference initialisation (planes / lines 0.1 * randn, nn.Linear default init, last head bias 0
--- what the constructors in models/ do).  No oracle code is involved."""
+-- what the constructors in models/ do).  Nothing from the test infrastructure is involved."""
 from __future__ import annotations
 
 import torch

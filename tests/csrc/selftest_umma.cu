@@ -1,8 +1,9 @@
+// TEST INFRASTRUCTURE (built into tests/lib/libdynrf_selftest.so, not into the product library).
 // Self-test entry point for the tcgen05 tile GEMM building block (used by tests/test_gpu_umma.py):
 // C[128][N] = A[128][K] x B[N][K]^T with operands staged in the K-major no-swizzle UMMA layout,
 // 1-pass TF32 or 3-pass split-TF32, accumulation in TMEM, K processed in chunks of 32.
-#include "dynrf_common.cuh"
-#include "dynrf_umma.cuh"
+#include "../../robust-dynrf_b200/csrc/dynrf_common.cuh"
+#include "../../robust-dynrf_b200/csrc/dynrf_umma.cuh"
 
 namespace dynrf {
 

@@ -151,3 +151,25 @@ def compare_pass(ref, got, thres=1e-4, check=True):
         assert rep["o_w_d_unnormalised"] <= 2e-5, rep
         assert rep["o_w_d"] <= 5e-5 + 300 * rep["d_weight"] / float(sr.min()), rep
     return rep
+
+
+def selftest_lib():
+    """tests/lib/libdynrf_selftest.so: the tcgen05 tile-GEMM self-test entry point (tests/csrc/selftest_umma.cu) -- test
+    infrastructure, kept out of the product library.  Built by __graft_entry__.build() (nvcc, no GPU needed)."""
+    import ctypes as C
+    import subprocess
+
+    src = os.path.join(ROOT, "tests", "csrc", "selftest_umma.cu")
+    out = os.path.join(ROOT, "tests", "lib", "libdynrf_selftest.so")
+    deps = [src] + [os.path.join(PKG, "csrc", f) for f in ("dynrf_common.cuh", "dynrf_umma.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(out) < os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC", "-shared",
+               "-o", out, src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    lib = C.CDLL(out)
+    lib.dynrf_selftest_umma_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.dynrf_selftest_umma_gemm.restype = C.c_int
+    return lib

@@ -12,7 +12,7 @@ gpu = pytest.mark.gpu
 @gpu
 @pytest.mark.parametrize("K,N", [(8, 64), (32, 64), (96, 64), (152, 64), (108, 128), (72, 32), (131, 128)])
 def test_umma_gemm(K, N):
-    lib = L.load()
+    lib = H.selftest_lib()
     g = torch.Generator().manual_seed(K * 1000 + N)
     A = torch.randn(128, K, generator=g).cuda()
     B = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
