@@ -329,6 +329,9 @@ def main():
     if mode == "auto":
         mode = "train" if TS.backward_available() else "fwd"
     N_RAYS, N_SAMPLES, GRID, RT = w["n_rays"], w["n_samples"], w["grid"], w["ray_type"]
+    strong = os.environ.get("DYNRF_STRONG", "0") == "1"     # strong scaling: the 4096-ray GLOBAL batch is split over the ranks
+    if strong:
+        N_RAYS = max(N_RAYS // world, 1)
 
     # identical parameters on every rank (replicated), a different ray shard per rank
     static, dyn = SY.make_models(GRID, RT, w["static_mode"], dev, seed=1)
@@ -461,9 +464,9 @@ def main():
         sb_flops = P * 2 * 2 * (152 * 64 + 64)  # density + blending MLPs, MAC x 2
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": config_dict(w, mode, world, not args.no_graph),
+            "config": dict(config_dict(w, mode, world, not args.no_graph), rays_per_gpu=N_RAYS),
             "roofline": roofline,
             "roofline_k1": roof_k1,
             "roofline_tensor": {"kernel": "k_dyn_sigma_blend_tc2 (a16+a17: 3-scale lookups + two 152->64->1 MLPs, tcgen05 3-pass split-TF32)",

@@ -368,7 +368,8 @@ int dynrf_dense_l1(const dynrf_vm_t* vm, int act, float shift, double* sum_out, 
 
 /* ---- optimiser: one-launch Adam over the flat gradient buffer of the train step (torch.optim.Adam semantics, no weight
  * decay / amsgrad; train.py:934, 2313-2325).  param_ptr [T]: device array of the parameters' storage pointers (uint64);
- * offset [T+1] (int64): prefix of numel in the flat grad / m / v buffers; blk0 [T+1] (int32) with
+ * offset [2T] (int64): [start, end) of every parameter in the flat grad / m / v buffers (starts may be padded for
+ * alignment); blk0 [T+1] (int32) with
  * blk0[t+1] - blk0[t] = dynrf_adam_blocks(numel_t); lr [T]; step [2]: step[0] float update count (incremented by the call),
  * step[1] uint32 scratch that the caller zero-initialises once. */
 int dynrf_adam_blocks(long long numel);

@@ -12,7 +12,7 @@ constexpr int kAdamPerBlock = kAdamThreads * 8;
 
 struct AdamTable {
   const unsigned long long* param_ptr;  // [T] device pointers (float*)
-  const long long* offset;              // [T + 1] prefix of numel in the flat buffers
+  const long long* offset;              // [2 T]: start, end of every parameter in the flat buffers (starts are aligned, so padded)
   const int* blk0;                      // [T + 1] first block of each tensor
   int T;
 };
@@ -28,7 +28,7 @@ k_adam_flat(AdamTable tb, const float* __restrict__ grad, float* __restrict__ m,
     else hi = mid;
   }
   const int t = lo;
-  const long long off = __ldg(tb.offset + t), n = __ldg(tb.offset + t + 1) - off;
+  const long long off = __ldg(tb.offset + 2 * t), n = __ldg(tb.offset + 2 * t + 1) - off;
   float* __restrict__ p = reinterpret_cast<float*>(__ldg(tb.param_ptr + t));
   const float step = *reinterpret_cast<volatile float*>(step_p) + 1.0f;   // this update's step number
   const float bc1 = 1.0f - powf(beta1, step), bc2 = 1.0f - powf(beta2, step);
@@ -67,7 +67,7 @@ extern "C" {
 
 int dynrf_adam_blocks(long long numel) { return (int)((numel + kAdamPerBlock - 1) / kAdamPerBlock); }
 
-/* param_ptr [T] (device array of float* as uint64), offset [T+1] (int64), blk0 [T+1] (int32; blk0[t+1]-blk0[t] =
+/* param_ptr [T] (device array of float* as uint64), offset [2T] (int64: start, end of each parameter), blk0 [T+1] (int32; blk0[t+1]-blk0[t] =
  * dynrf_adam_blocks(numel_t)), lr [T], step [2] (step[0]: float update count, incremented by the call; step[1]: uint32 scratch,
  * zero-initialised by the caller once), grad / m / v flat buffers. */
 int dynrf_adam_flat(const uint64_t* param_ptr, const int64_t* offset, const int32_t* blk0, int T, int total_blocks, const float* grad,

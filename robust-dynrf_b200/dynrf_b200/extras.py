@@ -156,8 +156,7 @@ class _TvFn(torch.autograd.Function):
         lib = L.load()
         n = len(tensors)
         dev = tensors[0].device
-        need = [t.requires_grad for t in tensors]
-        any_grad = any(need) and torch.is_grad_enabled()
+        any_grad = any(ctx.needs_input_grad[2:])     # (grad mode is off inside Function.forward: ask the ctx, not the tensors)
         xs, gs, Cs, Hs, Ws, ch, cw, counts = [], [], [], [], [], [], [], []
         for t, sc in zip(tensors, scales):
             x = t.detach()
@@ -190,7 +189,7 @@ class _TvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
-        return (None, None, *[None if g is None else g * gout for g in ctx.gs])
+        return (None, None, *[None if (g is None or not need) else g * gout for g, need in zip(ctx.gs, ctx.needs_input_grad[2:])])
 
 
 def tv_loss_vm(weight: float, planes: Sequence[torch.Tensor], lines: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -209,7 +208,7 @@ class _DenseL1Fn(torch.autograd.Function):
         planes, lines = tensors[:3], tensors[3:]
         vm = ops.vm_struct(planes, lines)
         dev = planes[0].device
-        any_grad = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+        any_grad = any(ctx.needs_input_grad[2:])
         total = torch.zeros(1, device=dev, dtype=torch.float64)
         gp = gl = gstruct = None
         if any_grad:
@@ -224,7 +223,7 @@ class _DenseL1Fn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
-        return (None, None, *[g * gout for g in ctx.grads])
+        return (None, None, *[(g * gout if need else None) for g, need in zip(ctx.grads, ctx.needs_input_grad[2:])])
 
 
 def dense_l1(model, planes, lines) -> torch.Tensor:

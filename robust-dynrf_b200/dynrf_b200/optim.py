@@ -26,16 +26,28 @@ def dense_storage(p: torch.Tensor) -> bool:
     return True
 
 
-def alias_grads(params: Sequence[torch.nn.Parameter]) -> torch.Tensor:
-    """One flat zero buffer; every p.grad becomes a view of it with p's own strides.  -> the flat buffer."""
-    dev = params[0].device
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
-    off = 0
+_ALIGN = 64   # floats: every view starts on a 256-byte boundary (the scatter kernels use 128-bit vector reductions on p.grad)
+
+
+def flat_offsets(params: Sequence[torch.Tensor]) -> List[int]:
+    """Start of every parameter in the flat buffer (+ total length as the last entry)."""
+    offs, off = [], 0
     for p in params:
+        offs.append(off)
+        off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+    return offs + [off]
+
+
+def alias_grads(params: Sequence[torch.nn.Parameter]) -> torch.Tensor:
+    """One flat zero buffer; every p.grad becomes a view of it with p's own strides (each view 256-byte aligned; the padding
+    stays zero and is ignored by FlatAdam and harmless in an all-reduce).  -> the flat buffer."""
+    dev = params[0].device
+    offs = flat_offsets(params)
+    flat = torch.zeros(offs[-1], device=dev)
+    for p, off in zip(params, offs):
         if not dense_storage(p):
             raise ValueError("FlatAdam needs densely stored parameters")
         p.grad = torch.as_strided(flat, p.shape, p.stride(), off)
-        off += p.numel()
     return flat
 
 
@@ -47,16 +59,18 @@ class FlatAdam:
         self.flat_grad = flat_grad
         dev = flat_grad.device
         T = len(self.params)
-        offs, blks = [0], [0]
-        for p in self.params:
-            if p.dtype != torch.float32 or not dense_storage(p) or p.storage_offset() != 0 and False:
+        offs, blks = flat_offsets(self.params), [0]
+        for p, off in zip(self.params, offs):
+            if p.dtype != torch.float32 or not dense_storage(p):
                 raise ValueError("FlatAdam: fp32, densely stored parameters only")
-            offs.append(offs[-1] + p.numel())
+            if p.grad is None or p.grad.data_ptr() != flat_grad.data_ptr() + 4 * off:
+                raise ValueError("FlatAdam: p.grad must be the view optim.alias_grads() created")
             blks.append(blks[-1] + lib.dynrf_adam_blocks(C.c_longlong(p.numel())))
         assert offs[-1] == flat_grad.numel()
         self.T, self.total_blocks = T, blks[-1]
-        self.ptrs = torch.tensor([p.data_ptr() for p in self.params], dtype=torch.int64, device=dev)   # re-read on rebuild()
-        self.offset = torch.tensor(offs, dtype=torch.int64, device=dev)
+        self.ptrs = torch.tensor([p.data_ptr() for p in self.params], dtype=torch.int64, device=dev)
+        # the kernel needs [start, end) of every parameter: ends differ from the next start by the alignment padding
+        self.offset = torch.tensor([v for p, off in zip(self.params, offs) for v in (off, off + p.numel())], dtype=torch.int64, device=dev)
         self.blk0 = torch.tensor(blks, dtype=torch.int32, device=dev)
         lrs = [float(lr)] * T if not isinstance(lr, (list, tuple)) else [float(x) for x in lr]
         self.lr = torch.tensor(lrs, dtype=torch.float32, device=dev)

@@ -139,8 +139,14 @@ def compare_pass(ref, got, thres=1e-4, check=True):
         assert rep["d_blending"] <= 2e-5, rep
         assert rep["d_xyz_prime"] <= 2e-5, rep
         assert rep["s_rgb"] <= 1e-4 and rep["d_rgb"] <= 1e-4, rep
+        sr_min = float((ref["fd"][4].sum(-1) + 1e-10).min())
         for k in ("rgb_full", "rgb_s", "rgb_d"):
-            assert rep[f"o_{k}_rel"] <= TOL_RGB_REL + 1e-4 * (rep["s_mask_flips"] + rep["d_mask_flips"] > 0), rep
+            tol = TOL_RGB_REL + 1e-4 * (rep["s_mask_flips"] + rep["d_mask_flips"] > 0)
+            if k == "rgb_d":
+                # rgb_map_d is composited with w_d / (sum w_d + 1e-10) (renderer.py:252): on a ray whose dynamic weights sum to
+                # ~1e-3 a 1e-7 error in one weight is a 1e-4 error in the normalised weight (same bound as o_w_d below)
+                tol += 300 * rep["d_weight"] / sr_min
+            assert rep[f"o_{k}_rel"] <= tol, (k, tol, rep)
         for k in ("acc_full", "acc_s", "acc_d", "w_full", "w_s", "dyn"):
             assert rep[f"o_{k}"] <= 5e-5, rep
         # w_d is divided by its own per-ray sum (renderer.py:252): on a ray whose dynamic weights sum to ~1e-3 a 1e-7 error

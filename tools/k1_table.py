@@ -3,7 +3,8 @@ at the 300^3 and 640^3 grids, train-order (random pixels over all frames, train.
 of one frame, renderer.py:1055) rays, both kernel variants (GEN=1: samples generated in-kernel; GEN=0: materialised inputs).
 
     python tools/k1_table.py time  > gpurun_out/k1_time.json        # CUDA events, L2 flushed between launches
-    ncu --set full --clock-control none -k regex:k_static_sigma_weight -o gpurun_out/k1 python tools/k1_table.py ncu
+    ncu --set full --metrics lts__t_bytes.sum,l1tex__t_bytes.sum,l1tex__data_pipe_lsu_wavefronts.sum --clock-control none \
+        -k regex:k_static_sigma_weight -o gpurun_out/k1 python tools/k1_table.py ncu
     python tools/k1_table.py merge gpurun_out/k1_time.json gpurun_out/k1.ncu-rep > profiles/r02_k1_table.json
 
 Algorithmic bytes per sample: 588 (GEN=1) / 605 (GEN=0).  Rays come from the ray generator the reference uses
@@ -96,7 +97,8 @@ def main():
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         warm = []
-        for i in range(20):      # L2-warm: back-to-back launches
+        for i in range(20):      # no flush between launches (tables L2-warm); the GPU idles between the tiny launches, so these
+                                 # are NOT faster than the flushed ones, whose 512 MiB fill keeps the clocks up
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             r = run()
@@ -119,12 +121,18 @@ METRICS = {"dram_read": "dram__bytes_read.sum", "dram_write": "dram__bytes_write
            "warps_active_pct": "sm__warps_active.avg.pct_of_peak_sustained_active"}
 
 
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9,
+         "nsecond": 1.0, "usecond": 1e3, "msecond": 1e6, "second": 1e9}
+
+
 def ncu_rows(rep, kernel_regex=None):
-    """-> list of per-launch dicts {kernel, metric: value} from an .ncu-rep (raw page)."""
+    """-> list of per-launch dicts {kernel, metric: value} from an .ncu-rep (raw page).  Bytes are returned in bytes and times
+    in ns: the raw page prints a units row (second line) and scales every column on its own."""
     cmd = ["ncu", "-i", rep, "--page", "raw", "--csv"]
     out = subprocess.run(cmd, capture_output=True, text=True).stdout
     rd = list(csv.reader(io.StringIO(out)))
-    hdr = rd[0]
+    hdr, units = rd[0], rd[1]
+    unit_of = dict(zip(hdr, units))
     res = []
     for r in rd[2:]:
         if len(r) != len(hdr):
@@ -134,7 +142,7 @@ def ncu_rows(rep, kernel_regex=None):
         for k, mname in METRICS.items():
             v = d.get(mname)
             try:
-                row[k] = float(v.replace(",", "")) if v not in (None, "") else None
+                row[k] = float(v.replace(",", "")) * _UNIT.get(unit_of.get(mname, ""), 1.0) if v not in (None, "") else None
             except ValueError:
                 row[k] = None
         res.append(row)
@@ -151,7 +159,7 @@ def merge(time_json, rep):
     out = []
     for row, m in zip(t["rows"], cold):
         alg = P * (588 if row["gen"] else 605)
-        ms = row["ms_cold_l2"]
+        ms = row["ms_cold_l2_median"]
         dram = (m["dram_read"] or 0) + (m["dram_write"] or 0)
         out.append(dict(row, algorithmic_bytes=alg, algorithmic_gbs=alg / ms / 1e6, algorithmic_frac_of_hbm_peak=alg / ms / 1e6 / peaks["hbm_gbs"],
                         dram_bytes=dram, dram_gbs=dram / ms / 1e6, dram_frac_of_hbm_peak=dram / ms / 1e6 / peaks["hbm_gbs"],
