@@ -28,7 +28,7 @@ from . import extras, ops
 def _depth_loss(pred, target):
     """compute_depth_loss (train.py:797-807): both maps shifted by their median and scaled by their mean abs deviation."""
     def nrm(x):
-        t = torch.median(x)
+        t = torch.sort(x).values[(x.numel() - 1) // 2]      # == torch.median(x) (lower median); sort is CUDA-graph capturable
         s = torch.mean(torch.abs(x - t))
         return (x - t) / (s + 1e-8)
 
