@@ -309,6 +309,7 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
 
+    sys.path.insert(0, os.path.join(ROOT, "robust-dynrf_b200"))
     if args.config == 5 or args.mode == "render":
         from dynrf_b200 import bench_extra as BX
 

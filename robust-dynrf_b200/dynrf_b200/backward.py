@@ -550,7 +550,10 @@ def train_fwd_bwd(step, rays, ts, target):
     if getattr(step, "opt", None) is None:
         _train_setup(step)
     step.flat_grad.zero_()
-    DIRECT_PLANE_GRADS[0] = True      # every p.grad is a live, zeroed view of step.flat_grad for the whole backward below
+    import os
+
+    # every p.grad is a live, zeroed view of step.flat_grad for the whole backward below (DYNRF_DIRECT_GRADS=0: A/B switch)
+    DIRECT_PLANE_GRADS[0] = os.environ.get("DYNRF_DIRECT_GRADS", "1") == "1"
     rays_s = rays
     if getattr(step, "rays_grad", False):
         # pose / focal optimisation (cfg 3/4): the rays carry requires_grad; as in the reference's passes 5-9 the gradient reaches

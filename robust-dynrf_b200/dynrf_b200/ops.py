@@ -288,8 +288,19 @@ def field_cfg(aabb: torch.Tensor, near_far, distance_scale, weight_thres, act: s
 # ----------------------------------------------------------------------------- a1-a3 sampling
 
 
+_ZVEC_EVAL: Dict[tuple, torch.Tensor] = {}
+
+
 def make_zvec(cfg: L.FieldCfgT, n_samples: int, ray_type: str, is_train: bool, device) -> torch.Tensor:
+    """The batch-wide depth vector (models/tensorBase.py:490-492, 530-548).  Evaluation mode is deterministic, so its vector is
+    computed once per (ray type, near, far, S, device) -- one launch less on every no-grad pass; callers never write to it."""
     lib = L.load()
+    key = None
+    if not is_train and not torch.cuda.is_current_stream_capturing():
+        key = (ray_type, float(cfg.near_), float(cfg.far_), int(n_samples), str(device))
+        hit = _ZVEC_EVAL.get(key)
+        if hit is not None:
+            return hit
     zvec = torch.empty(n_samples, device=device, dtype=torch.float32)
     if ray_type == "ndc":
         jit = torch.rand(n_samples, device=device) if is_train else None  # one draw shared by all rays
@@ -302,7 +313,12 @@ def make_zvec(cfg: L.FieldCfgT, n_samples: int, ray_type: str, is_train: bool, d
                 "dynrf_zvec_contract")
     else:
         raise NotImplementedError(
-            "ray_type must be 'ndc' or 'contract' (sample_ray, models/tensorBase.py:501-522, is unused by every config)")
+            "ray_type must be 'ndc' or 'contract' (the aabb-marching sampler is TensorBase.sample_ray; renderer.sampleXYZ's own "
+            "dispatch to it tiles the per-ray depths N times, renderer.py:168, and no config uses it)")
+    if key is not None:
+        if len(_ZVEC_EVAL) > 64:
+            _ZVEC_EVAL.clear()
+        _ZVEC_EVAL[key] = zvec
     return zvec
 
 

@@ -80,6 +80,12 @@ class FlatAdam:
         self.betas, self.eps = betas, eps
 
     def step(self):
+        from . import ops
+
+        # the kernel moves the weights without touching their autograd version counters: every packed-operand cache
+        # (ops.PackedLayer & co.) keys on this epoch, so bump it -- also BEFORE a CUDA-graph capture, so that the pack kernels
+        # of the next forward are part of the captured step
+        ops.PARAM_EPOCH[0] += 1
         L.check(L.load().dynrf_adam_flat(_p(self.ptrs), _p(self.offset), _p(self.blk0), self.T, self.total_blocks, _p(self.flat_grad),
                                          _p(self.m), _p(self.v), _p(self.state), _p(self.lr), float(self.betas[0]), float(self.betas[1]),
                                          float(self.eps), _stream()), "dynrf_adam_flat")

@@ -21,14 +21,15 @@ def test_train9_step_runs_and_reaches_every_parameter(graph):
     step = T9.Train9(static, dyn, 32, "ndc", 27, 48, 5, focal=40.0, graph=graph, tv_weight=1e-3)
     g = torch.Generator().manual_seed(0)
     batch = T9.synth_batch(256, 27, 48, 5, g, torch.device(DEV))
-    before = {n: p.detach().clone() for n, p in list(static.named_parameters()) + list(dyn.named_parameters())}
+    named = [("s:" + n, p) for n, p in static.named_parameters()] + [("d:" + n, p) for n, p in dyn.named_parameters()]
+    before = {n: p.detach().clone() for n, p in named}
     p0, f0 = step.poses.detach().clone(), step.focal.detach().clone()
     for _ in range(2):
         out = step(batch)
     torch.cuda.synchronize()
     assert out.shape == (256, 5) and bool(torch.isfinite(out).all())
     assert bool(torch.isfinite(step.flat_grad).all())
-    moved = {n: float((p.detach() - before[n]).abs().max()) for n, p in list(static.named_parameters()) + list(dyn.named_parameters())}
+    moved = {n: float((p.detach() - before[n]).abs().max()) for n, p in named}
     stuck = [n for n, v in moved.items() if v == 0.0]
     assert not stuck, f"parameters that never received a gradient: {stuck}"
     assert float((step.poses.detach() - p0).abs().max()) > 0 and float((step.focal.detach() - f0).abs().max()) > 0
