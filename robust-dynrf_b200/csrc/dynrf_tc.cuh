@@ -45,12 +45,23 @@ __device__ __forceinline__ float4 vm_group_f(const float* __restrict__ plane, co
 
 // write 4 consecutive operand rows (quad q of the chunk) for sample m as split tf32, one 16-byte store each
 // feature-major global copy of one quad: rows r0..r0+3 of gT (row stride ld) at column `col`
+// The feature-major activation streams (0.3 - 1.5 GB per launch at cfg 2) are written once and read once by a later kernel; with
+// DYNRF_STREAM_HINTS they use the streaming (evict-first) cache policy so that they do not push the parameter tables and the
+// gradient tables -- the targets of the gathers and of the L2 reductions -- out of the 126 MB L2.
+#ifdef DYNRF_STREAM_HINTS
+#define DYNRF_ST_STREAM(ptr, val) __stcs((ptr), (val))
+#define DYNRF_LD_STREAM(ptr) __ldcs(ptr)
+#else
+#define DYNRF_ST_STREAM(ptr, val) (*(ptr) = (val))
+#define DYNRF_LD_STREAM(ptr) __ldg(ptr)
+#endif
+
 __device__ __forceinline__ void store_quad_g(float* __restrict__ gT, int ld, int r0, int col, float4 v) {
   float* p = gT + (size_t)r0 * ld + col;
-  p[0] = v.x;
-  p[ld] = v.y;
-  p[2 * (size_t)ld] = v.z;
-  p[3 * (size_t)ld] = v.w;
+  DYNRF_ST_STREAM(p, v.x);
+  DYNRF_ST_STREAM(p + ld, v.y);
+  DYNRF_ST_STREAM(p + 2 * (size_t)ld, v.z);
+  DYNRF_ST_STREAM(p + 3 * (size_t)ld, v.w);
 }
 
 __device__ __forceinline__ void store_quad(float* __restrict__ buf, int m, int q, float4 v) {

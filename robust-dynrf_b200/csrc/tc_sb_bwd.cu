@@ -220,7 +220,7 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
         float po = 0.f;
         if (SAVED) {
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) h[jj] = __ldg(a.HT + (size_t)(cb * 32 + jj) * ld + i0g + em);   // already relu'd and masked
+          for (int jj = 0; jj < 32; ++jj) h[jj] = DYNRF_LD_STREAM(a.HT + (size_t)(cb * 32 + jj) * ld + i0g + em);   // already relu'd and masked
         } else {
           umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 32, h);
 #pragma unroll

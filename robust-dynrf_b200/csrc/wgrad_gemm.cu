@@ -40,7 +40,11 @@ __device__ __forceinline__ void prefetch_rows(Pref<ROWS>& pf, const float* __res
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (item < ROWS * kWgQ && row < nrows && p < P) {
       const float* s = src + (size_t)row * ld + p;
+#ifdef DYNRF_STREAM_HINTS
+      if (p + 3 < P) v = __ldcs(reinterpret_cast<const float4*>(s));   // read-once stream: evict-first
+#else
       if (p + 3 < P) v = __ldg(reinterpret_cast<const float4*>(s));
+#endif
       else {
         v.x = __ldg(s);
         if (p + 1 < P) v.y = __ldg(s + 1);

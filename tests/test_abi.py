@@ -72,3 +72,20 @@ def test_state_dict_matches_reference_keys(golden_case):
     # channel-last storage, logical NCHW shape
     p = static.density_plane[0]
     assert p.shape[1] == 16 and p.stride(1) == 1
+
+
+def test_bench_workload_is_the_test_helpers_model():
+    """bench.py's native arm builds its models with dynrf_b200/synth.py (no test infrastructure on that path); the CPU arm and the
+    tests use tests/helpers.build_pair.  Both must be the same model (same generator, same draw order)."""
+    import torch
+
+    from dynrf_b200 import synth
+
+    for rt, mode, grid in (("ndc", "MLP_Fea", [21, 24, 18]), ("contract", "MLP_Fea_TimeEmbedding", [16, 19, 20])):
+        case = helpers.build_pair(grid, 8, 8, ray_type=rt, static_mode=mode, seed=1)
+        gen = torch.Generator().manual_seed(1)
+        a = synth.init_state_dict(False, mode, grid, gen)
+        b = synth.init_state_dict(True, mode, grid, gen)
+        assert a.keys() == case["sd_static"].keys() and b.keys() == case["sd_dynamic"].keys()
+        assert all(torch.equal(a[k], case["sd_static"][k]) for k in a)
+        assert all(torch.equal(b[k], case["sd_dynamic"][k]) for k in b)

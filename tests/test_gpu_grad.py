@@ -123,7 +123,7 @@ def _check_parameter_gradients(case):
             assert ref is not None, name
             assert p.grad is not None, f"{tag}:{name} got no gradient"
             assert p.grad.shape == ref.shape
-            worst[f"{tag}:{name}"] = _grad_ok(p.grad.cpu(), ref)
+            worst[f"{tag}:{name}"] = _grad_ok(p.grad.cpu(), ref, n_samples=case["rays"].shape[0] * case["n_samples"])
     bad = {k: v for k, v in worst.items() if not v[0]}
     print(sorted(((k, v[1], v[2]) for k, v in worst.items()), key=lambda kv: -kv[1])[:8])
     assert not bad, bad

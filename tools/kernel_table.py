@@ -16,7 +16,7 @@ from k1_table import ncu_rows  # noqa: E402
 
 def norm(name):
     name = re.sub(r"\((bool|int)\)", "", name)
-    name = re.sub(r"^dynrf::", "", name)
+    name = re.sub(r"^(void\s+)?(dynrf::)?", "", name)
     name = re.sub(r"\(.*$", "", name)          # drop the argument list
     return name.replace(" ", "")
 
