@@ -18,7 +18,7 @@ def main():
     h = rows[hdr_i]
     kn, mv, mu = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
     scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}
-    cnt, tim = collections.Counter(), collections.Counter()
+    seq = []
     for r in rows[hdr_i + 1:]:
         if len(r) <= mv:
             continue
@@ -31,9 +31,18 @@ def main():
         name = re.sub(r"\(.*$", "", name).strip()
         if name.startswith("at::") or "at::native" in name:
             name = "ATen: " + re.sub(r"<.*", "", name.replace("at::native::", "").replace("at::", ""))[:60]
+        seq.append((name, t))
+    # whole steps only: a step ends with the optimiser kernel (k_adam_flat; round 1: the last multi_tensor_apply of torch's Adam)
+    ends = [i for i, (n, _) in enumerate(seq) if n == "k_adam_flat"]
+    if len(ends) >= 2:
+        seq = seq[ends[0] + 1: ends[-1] + 1]
+        steps = len(ends) - 1
+    else:
+        steps = int(sys.argv[2]) if len(sys.argv) > 2 else max(1, sum(1 for n, _ in seq if n == "k_composite"))
+    cnt, tim = collections.Counter(), collections.Counter()
+    for name, t in seq:
         cnt[name] += 1
         tim[name] += t
-    steps = cnt.get("k_composite", 0) or (int(sys.argv[2]) if len(sys.argv) > 2 else 1)
     total = sum(tim.values())
     out = [{"kernel": k, "launches_per_step": cnt[k] / steps, "us_per_step": v / steps, "share": v / total}
            for k, v in sorted(tim.items(), key=lambda kv: -kv[1])]
