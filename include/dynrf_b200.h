@@ -13,8 +13,9 @@
  *   - the library allocates nothing persistent, never synchronises the device, never
  *     throws, never exits.  All work is enqueued on `stream` (a cudaStream_t passed as void*).
  *   - return value: 0 = OK; >0 = cudaError_t from the launch; <0 = DYNRF_E_* argument error.
- *   - planes are channel-LAST: plane i is [H][W][C] for the reference parameter of shape
- *     (1,C,H,W) (i.e. torch.channels_last strides); line i is [L][C] for (1,C,L,1).
+ *   - planes are channel-LAST: the C values of a texel are contiguous; the order of the two texel dimensions is given per
+ *     plane by dynrf_vm_t.sv / .su (the drop-in modules store plane 0 as [H][W][C] and planes 1, 2 as [W][H][C]);
+ *     line i is [L][C] for (1,C,L,1).
  *     matMode = {{0,1},{0,2},{1,2}}, vecMode = {2,1,0} (models/tensorBase.py:326-327):
  *     plane i has W = G[matMode[i][0]], H = G[matMode[i][1]]; line i has L = G[vecMode[i]].
  *   - MLP layers are "packed": wt is [Kpad][Npad] (input-major, zero padded) built by
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DYNRF_ABI_VERSION 1
+#define DYNRF_ABI_VERSION 2
 
 #define DYNRF_E_ARG (-1)         /* null pointer / non-positive size */
 #define DYNRF_E_UNSUPPORTED (-2) /* configuration outside the compiled kernels (component counts, widths) */
@@ -47,9 +48,14 @@ extern "C" {
 
 /* One vector-matrix decomposed quantity (density, blending or appearance). */
 typedef struct {
-  const float* plane[3]; /* [H][W][C] */
+  const float* plane[3]; /* channel-last texels, see sv / su */
   const float* line[3];  /* [L][C]    */
   int32_t C[3], H[3], W[3], L[3];
+  /* texel strides of plane i: element (h, w, c) lives at ((h * sv[i] + w * su[i]) * C[i] + c).
+   * [H][W][C] ("x-fastest") is sv = W, su = 1; [W][H][C] ("z-fastest") is sv = 1, su = H.  The host stores plane 0 (x, y)
+   * x-fastest and planes 1, 2 (x, z) / (y, z) z-fastest: consecutive samples of a ray are consecutive lanes of a warp and
+   * advance mostly in z, so their taps in the two z planes fall into a few contiguous 128-byte lines instead of 32 rows. */
+  int32_t sv[3], su[3];
 } dynrf_vm_t;
 
 /* Gradient buffers with the layout of dynrf_vm_t (accumulated into with atomics; caller zeroes). */

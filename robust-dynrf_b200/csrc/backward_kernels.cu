@@ -339,7 +339,7 @@ k_static_density_bwd(dynrf_field_cfg_t cfg, dynrf_vm_t vm, dynrf_vm_grad_t gvm, 
       plane_axes(pl, u, v, l);
       const Tap1 tu = make_tap(xn[u], vm.W[pl], 1), tv = make_tap(xn[v], vm.H[pl], 1), tl = make_tap(xn[l], vm.L[pl], 1);
       for (int c = 0; c < vm.C[pl]; c += 4) {
-        const float4 r = vm_group(vm.plane[pl], vm.line[pl], vm.C[pl], vm.W[pl], tu, tv, tl, c);
+        const float4 r = vm_group(vm.plane[pl], vm.line[pl], vm.C[pl], plane_st(vm, pl), tu, tv, tl, c);
         feat += (r.x + r.y) + (r.z + r.w);
       }
     }
@@ -355,7 +355,7 @@ k_static_density_bwd(dynrf_field_cfg_t cfg, dynrf_vm_t vm, dynrf_vm_grad_t gvm, 
     plane_axes(pl, u, v, l);
     const Tap1 tu = make_tap(xn[u], vm.W[pl], 1), tv = make_tap(xn[v], vm.H[pl], 1), tl = make_tap(xn[l], vm.L[pl], 1);
     for (int c = 0; c < vm.C[pl]; c += 4) {
-      const float3 r = vm_group_bwd_w(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], vm.C[pl], vm.W[pl], tu, tv, tl, c, g4, act,
+      const float3 r = vm_group_bwd_w(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], vm.C[pl], plane_st(vm, pl), tu, tv, tl, c, g4, act,
                                       threadIdx.x & 31, nullptr, gxyz != nullptr);
       gacc[u] += r.x;
       gacc[v] += r.y;
@@ -957,6 +957,7 @@ int dynrf_composite_bwd(int ray_type, int white_bg, const float* rgb_s, const fl
 int dynrf_static_density_bwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density, const dynrf_vm_grad_t* gdensity,
                              const float* xyz, const uint8_t* valid, const float* sigma, const float* gsigma, int N, int S,
                              float* gxyz, void* stream) {
+  if (density && !dynrf_vm_layout_ok(density)) return DYNRF_E_UNSUPPORTED;
   if (!cfg || !density || !gdensity || !xyz || !valid || !sigma || !gsigma || N <= 0 || S <= 0) return DYNRF_E_ARG;
   const int P = N * S;
   k_static_density_bwd<<<(P + 127) / 128, 128, 0, S_(stream)>>>(*cfg, *density, *gdensity, xyz, valid, sigma, gsigma, P, gxyz);
@@ -992,6 +993,7 @@ int dynrf_dyn_mlp_bwd(const dynrf_field_cfg_t* cfg, int mode, const dynrf_vm_t* 
                       const dynrf_layer_t* l1, const dynrf_layer_t* l2, const float* wb1f, const float* xyz, const float* xyz_prime,
                       const uint8_t* valid, const float* tfeat, int N, int S, const float* gout, const dynrf_layer_grad_t* g1,
                       const dynrf_layer_grad_t* g2, float* gxp, void* stream) {
+  if (vm && !dynrf_vm_layout_ok(vm)) return DYNRF_E_UNSUPPORTED;
   if (!cfg || !vm || !gvm || !l1 || !l2 || !wb1f || !xyz || !xyz_prime || !valid || !tfeat || !gout || !g1 || !g2 || !gxp ||
       N <= 0 || S <= 0)
     return DYNRF_E_ARG;
@@ -1011,6 +1013,7 @@ int dynrf_dyn_app_bwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* app, const
                       const int32_t* active_idx, const int32_t* active_count, const float* grgb, const dynrf_layer_grad_t* gB,
                       const dynrf_layer_grad_t* g1, const dynrf_layer_grad_t* g2, const dynrf_layer_grad_t* g3, float* gxp,
                       void* stream) {
+  if (app && !dynrf_vm_layout_ok(app)) return DYNRF_E_UNSUPPORTED;
   if (!cfg || !app || !gapp || !basis || !l1 || !l2 || !l3 || !wb2 || !wb1f || !wbB || !rays || !xyz || !xyz_prime || !tfeat ||
       !active_idx || !active_count || !grgb || !gB || !g1 || !g2 || !g3 || !gxp || N <= 0 || S <= 0)
     return DYNRF_E_ARG;
@@ -1031,6 +1034,7 @@ int dynrf_static_app_bwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* app, co
                          const int32_t* active_idx, const int32_t* active_count, const float* grgb, const dynrf_layer_grad_t* gB,
                          const dynrf_layer_grad_t* g1, const dynrf_layer_grad_t* g2, const dynrf_layer_grad_t* g3, float* gxyz,
                          float* gviewdir, void* stream) {
+  if (app && !dynrf_vm_layout_ok(app)) return DYNRF_E_UNSUPPORTED;
   if (!cfg || !app || !gapp || !basis || !l1 || !l2 || !l3 || !wb2 || !wb1 || !wbB || !rays || !xyz || !active_idx ||
       !active_count || !grgb || !gB || !g1 || !g2 || !g3 || N <= 0 || S <= 0)
     return DYNRF_E_ARG;

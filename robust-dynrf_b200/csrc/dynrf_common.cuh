@@ -15,6 +15,21 @@
     if (_e != cudaSuccess) return (int)_e;            \
   } while (0)
 
+// host-side: every plane must be channel-last with one of the two texel orders (see dynrf_vm_t.sv / .su)
+static inline int dynrf_vm_layout_ok(const dynrf_vm_t* vm) {
+  for (int i = 0; i < 3; ++i) {
+    const bool xfast = vm->sv[i] == vm->W[i] && vm->su[i] == 1;
+    const bool zfast = vm->sv[i] == 1 && vm->su[i] == vm->H[i];
+    if (!xfast && !zfast && !(vm->H[i] == 1 || vm->W[i] == 1)) return 0;
+  }
+  return 1;
+}
+static inline int dynrf_vm_same_layout(const dynrf_vm_t* a, const dynrf_vm_t* b) {
+  for (int i = 0; i < 3; ++i)
+    if (a->sv[i] != b->sv[i] || a->su[i] != b->su[i]) return 0;
+  return 1;
+}
+
 namespace dynrf {
 
 constexpr int kTileM = 128;        // samples per MLP tile
@@ -98,15 +113,22 @@ __device__ __forceinline__ float4 mul4(float4 v, float w) { return make_float4(v
 __device__ __forceinline__ float4 mul44(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 
 // 4 channels [c..c+3] of plane (bilinear) x line (linear): one "channel group" product.
-// plane: [H][W][C]; tu indexes W, tv indexes H.  Weight order nw, ne, sw, se as ATen.
-__device__ __forceinline__ float4 vm_group(const float* __restrict__ plane, const float* __restrict__ line, int C, int W,
+// plane: channel-last texels with strides st; tu indexes W, tv indexes H.  Weight order nw, ne, sw, se as ATen.
+// texel strides of one plane (dynrf_vm_t.sv / .su): element (v, u) lives at (v * sv + u * su) * C
+struct PlaneSt {
+  int sv, su;
+};
+__device__ __forceinline__ PlaneSt plane_st(const dynrf_vm_t& vm, int pl) { return PlaneSt{vm.sv[pl], vm.su[pl]}; }
+
+__device__ __forceinline__ float4 vm_group(const float* __restrict__ plane, const float* __restrict__ line, int C, PlaneSt st,
                                            const Tap1& tu, const Tap1& tv, const Tap1& tl, int c) {
   const float wnw = tu.w0 * tv.w0, wne = tu.w1 * tv.w0, wsw = tu.w0 * tv.w1, wse = tu.w1 * tv.w1;
-  const size_t r0 = (size_t)tv.i0 * W, r1 = (size_t)tv.i1 * W;
-  float4 p = mul4(ldg4(plane + (r0 + tu.i0) * C + c), wnw);
-  p = fma4(ldg4(plane + (r0 + tu.i1) * C + c), wne, p);
-  p = fma4(ldg4(plane + (r1 + tu.i0) * C + c), wsw, p);
-  p = fma4(ldg4(plane + (r1 + tu.i1) * C + c), wse, p);
+  const size_t r0 = (size_t)tv.i0 * st.sv, r1 = (size_t)tv.i1 * st.sv;
+  const size_t c0 = (size_t)tu.i0 * st.su, c1 = (size_t)tu.i1 * st.su;
+  float4 p = mul4(ldg4(plane + (r0 + c0) * C + c), wnw);
+  p = fma4(ldg4(plane + (r0 + c1) * C + c), wne, p);
+  p = fma4(ldg4(plane + (r1 + c0) * C + c), wsw, p);
+  p = fma4(ldg4(plane + (r1 + c1) * C + c), wse, p);
   float4 l = mul4(ldg4(line + (size_t)tl.i0 * C + c), tl.w0);
   l = fma4(ldg4(line + (size_t)tl.i1 * C + c), tl.w1, l);
   return mul44(p, l);

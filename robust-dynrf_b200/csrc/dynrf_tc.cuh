@@ -30,14 +30,15 @@ __device__ __forceinline__ TapF tapf(float x, int n, int s) {
   const Tap1 t = make_tap(x, n, s);
   return TapF{t.i0, t.i1, t.w0, t.w1};
 }
-__device__ __forceinline__ float4 vm_group_f(const float* __restrict__ plane, const float* __restrict__ line, int C, int W,
+__device__ __forceinline__ float4 vm_group_f(const float* __restrict__ plane, const float* __restrict__ line, int C, PlaneSt st,
                                              const TapF& tu, const TapF& tv, const TapF& tl, int c) {
   const float wnw = tu.w0 * tv.w0, wne = tu.w1 * tv.w0, wsw = tu.w0 * tv.w1, wse = tu.w1 * tv.w1;
-  const size_t r0 = (size_t)tv.i0 * W, r1 = (size_t)tv.i1 * W;
-  float4 p = mul4(ldg4(plane + (r0 + tu.i0) * C + c), wnw);
-  p = fma4(ldg4(plane + (r0 + tu.i1) * C + c), wne, p);
-  p = fma4(ldg4(plane + (r1 + tu.i0) * C + c), wsw, p);
-  p = fma4(ldg4(plane + (r1 + tu.i1) * C + c), wse, p);
+  const size_t r0 = (size_t)tv.i0 * st.sv, r1 = (size_t)tv.i1 * st.sv;
+  const size_t c0 = (size_t)tu.i0 * st.su, c1 = (size_t)tu.i1 * st.su;
+  float4 p = mul4(ldg4(plane + (r0 + c0) * C + c), wnw);
+  p = fma4(ldg4(plane + (r0 + c1) * C + c), wne, p);
+  p = fma4(ldg4(plane + (r1 + c0) * C + c), wsw, p);
+  p = fma4(ldg4(plane + (r1 + c1) * C + c), wse, p);
   float4 l = mul4(ldg4(line + (size_t)tl.i0 * C + c), tl.w0);
   l = fma4(ldg4(line + (size_t)tl.i1 * C + c), tl.w1, l);
   return mul44(p, l);

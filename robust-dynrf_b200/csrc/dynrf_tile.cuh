@@ -41,7 +41,7 @@ __device__ __forceinline__ void gather_vm_rows(const dynrf_vm_t& vm, const float
     }
     for (int g = (part - q % NPART + NPART) % NPART; g < ng; g += NPART) {
       float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (act) r = vm_group(vm.plane[pl], vm.line[pl], C, vm.W[pl], tu, tv, tl, g * 4);
+      if (act) r = vm_group(vm.plane[pl], vm.line[pl], C, plane_st(vm, pl), tu, tv, tl, g * 4);
       float* a = A + (size_t)(row_base + coff + g * 4) * LD + m;
       a[0] = r.x;
       a[LD] = r.y;
@@ -61,12 +61,13 @@ __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.
 // Adds into the plane / line gradients (vector reductions) and returns d loss / d (xu, xv, xl) in
 // normalised-coordinate units.  Out-of-range taps carry value 0 (zeros padding) and get no gradient.
 __device__ __forceinline__ float3 vm_group_bwd(const float* __restrict__ plane, const float* __restrict__ line,
-                                               float* __restrict__ gplane, float* __restrict__ gline, int C, int W,
+                                               float* __restrict__ gplane, float* __restrict__ gline, int C, PlaneSt st,
                                                const Tap1& tu, const Tap1& tv, const Tap1& tl, int c, float4 g,
                                                float4* feat = nullptr /* optional: the forward value plane*line of the group */,
                                                bool need_gx = true /* false: skip d/d(coords), returns zeros */) {
-  const size_t o00 = ((size_t)tv.i0 * W + tu.i0) * C + c, o01 = ((size_t)tv.i0 * W + tu.i1) * C + c;
-  const size_t o10 = ((size_t)tv.i1 * W + tu.i0) * C + c, o11 = ((size_t)tv.i1 * W + tu.i1) * C + c;
+  const size_t r0_ = (size_t)tv.i0 * st.sv, r1_ = (size_t)tv.i1 * st.sv, c0_ = (size_t)tu.i0 * st.su, c1_ = (size_t)tu.i1 * st.su;
+  const size_t o00 = (r0_ + c0_) * C + c, o01 = (r0_ + c1_) * C + c;
+  const size_t o10 = (r1_ + c0_) * C + c, o11 = (r1_ + c1_) * C + c;
   const bool b00 = tu.v0 && tv.v0, b01 = tu.v1 && tv.v0, b10 = tu.v0 && tv.v1, b11 = tu.v1 && tv.v1;
   const float4 P00 = b00 ? ldg4(plane + o00) : zero4(), P01 = b01 ? ldg4(plane + o01) : zero4();
   const float4 P10 = b10 ? ldg4(plane + o10) : zero4(), P11 = b11 ? ldg4(plane + o11) : zero4();
@@ -140,11 +141,12 @@ __device__ __forceinline__ int tap_key(const Tap1& t, bool act) {
 
 // Same contract as vm_group_bwd, but must be called by all 32 lanes of the warp (act = false for idle lanes).
 __device__ __forceinline__ float3 vm_group_bwd_agg(const float* __restrict__ plane, const float* __restrict__ line,
-                                                   float* __restrict__ gplane, float* __restrict__ gline, int C, int W,
+                                                   float* __restrict__ gplane, float* __restrict__ gline, int C, PlaneSt st,
                                                    const Tap1& tu, const Tap1& tv, const Tap1& tl, int c, float4 g, bool act,
                                                    int lane, float4* feat = nullptr, bool need_gx = true) {
-  const size_t o00 = ((size_t)tv.i0 * W + tu.i0) * C + c, o01 = ((size_t)tv.i0 * W + tu.i1) * C + c;
-  const size_t o10 = ((size_t)tv.i1 * W + tu.i0) * C + c, o11 = ((size_t)tv.i1 * W + tu.i1) * C + c;
+  const size_t r0_ = (size_t)tv.i0 * st.sv, r1_ = (size_t)tv.i1 * st.sv, c0_ = (size_t)tu.i0 * st.su, c1_ = (size_t)tu.i1 * st.su;
+  const size_t o00 = (r0_ + c0_) * C + c, o01 = (r0_ + c1_) * C + c;
+  const size_t o10 = (r1_ + c0_) * C + c, o11 = (r1_ + c1_) * C + c;
   const bool b00 = act && tu.v0 && tv.v0, b01 = act && tu.v1 && tv.v0, b10 = act && tu.v0 && tv.v1, b11 = act && tu.v1 && tv.v1;
   const float4 P00 = b00 ? ldg4(plane + o00) : zero4(), P01 = b01 ? ldg4(plane + o01) : zero4();
   const float4 P10 = b10 ? ldg4(plane + o10) : zero4(), P11 = b11 ? ldg4(plane + o11) : zero4();
@@ -196,17 +198,17 @@ __device__ __forceinline__ float3 vm_group_bwd_agg(const float* __restrict__ pla
 // the incoherent taps of a randomly initialised warp field (with layer-1 recompute in the same kernel it was a 3 % loss).
 constexpr bool kAggScatter = true;
 __device__ __forceinline__ float3 vm_group_bwd_w(const float* __restrict__ plane, const float* __restrict__ line,
-                                                 float* __restrict__ gplane, float* __restrict__ gline, int C, int W, const Tap1& tu,
+                                                 float* __restrict__ gplane, float* __restrict__ gline, int C, PlaneSt st, const Tap1& tu,
                                                  const Tap1& tv, const Tap1& tl, int c, float4 g, bool act, int lane,
                                                  float4* feat = nullptr, bool need_gx = true) {
   if constexpr (kAggScatter) {
-    return vm_group_bwd_agg(plane, line, gplane, gline, C, W, tu, tv, tl, c, g, act, lane, feat, need_gx);
+    return vm_group_bwd_agg(plane, line, gplane, gline, C, st, tu, tv, tl, c, g, act, lane, feat, need_gx);
   } else {
     if (!act) {
       if (feat) *feat = zero4();
       return make_float3(0.f, 0.f, 0.f);
     }
-    return vm_group_bwd(plane, line, gplane, gline, C, W, tu, tv, tl, c, g, feat, need_gx);
+    return vm_group_bwd(plane, line, gplane, gline, C, st, tu, tv, tl, c, g, feat, need_gx);
   }
 }
 
@@ -237,7 +239,7 @@ __device__ __forceinline__ void scatter_vm_rows(const dynrf_vm_t& vm, const dynr
       float3 r;
       if (Afeat) {   // fused recompute: the taps are loaded once for the scatter and for the forward value
         float4 fv;
-        r = vm_group_bwd_w(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], C, vm.W[pl], tu, tv, tl, g * 4, gg, act, tid & 31, &fv,
+        r = vm_group_bwd_w(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], C, plane_st(vm, pl), tu, tv, tl, g * 4, gg, act, tid & 31, &fv,
                            gxs != nullptr);
         float* fa = Afeat + (size_t)(row_base + coff + g * 4) * LD + m;
         fa[0] = fv.x;
@@ -245,7 +247,7 @@ __device__ __forceinline__ void scatter_vm_rows(const dynrf_vm_t& vm, const dynr
         fa[2 * LD] = fv.z;
         fa[3 * LD] = fv.w;
       } else {
-        r = vm_group_bwd_w(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], C, vm.W[pl], tu, tv, tl, g * 4, gg, act, tid & 31);
+        r = vm_group_bwd_w(vm.plane[pl], vm.line[pl], gvm.plane[pl], gvm.line[pl], C, plane_st(vm, pl), tu, tv, tl, g * 4, gg, act, tid & 31);
       }
       gacc[u] += r.x;
       gacc[v] += r.y;

@@ -389,7 +389,7 @@ k_dense_l1(dynrf_vm_t vm, int act, float shift, int Gx, int Gy, int Gz, int zchu
 #pragma unroll
   for (int c = 0; c < 16; ++c) P0[c] = 0.f;
   if (in) {
-    const float* p = vm.plane[0] + ((size_t)y * Gx + x) * 16;
+    const float* p = vm.plane[0] + ((size_t)y * vm.sv[0] + (size_t)x * vm.su[0]) * 16;              // plane 0: (h, w) = (y, x)
 #pragma unroll
     for (int c = 0; c < 16; c += 4) {
       const float4 v = ldg4(p + c);
@@ -414,8 +414,8 @@ k_dense_l1(dynrf_vm_t vm, int act, float shift, int Gx, int Gy, int Gz, int zchu
     }
     float4 P1 = make_float4(0.f, 0.f, 0.f, 0.f), P2 = P1;
     if (in) {
-      P1 = ldg4(vm.plane[1] + ((size_t)z * Gx + x) * 4);
-      P2 = ldg4(vm.plane[2] + ((size_t)z * Gy + y) * 4);
+      P1 = ldg4(vm.plane[1] + ((size_t)z * vm.sv[1] + (size_t)x * vm.su[1]) * 4);     // plane 1: (h, w) = (z, x)
+      P2 = ldg4(vm.plane[2] + ((size_t)z * vm.sv[2] + (size_t)y * vm.su[2]) * 4);     // plane 2: (h, w) = (z, y)
     }
     float v = 0.f;
 #pragma unroll
@@ -458,7 +458,7 @@ k_dense_l1(dynrf_vm_t vm, int act, float shift, int Gx, int Gy, int Gz, int zchu
         r.x += __shfl_xor_sync(0xffffffffu, r.x, o); r.y += __shfl_xor_sync(0xffffffffu, r.y, o);
         r.z += __shfl_xor_sync(0xffffffffu, r.z, o); r.w += __shfl_xor_sync(0xffffffffu, r.w, o);
       }
-      if (ty == 0 && x < Gx) red_add4g(gp1 + ((size_t)z * Gx + x) * 4, r);
+      if (ty == 0 && x < Gx) red_add4g(gp1 + ((size_t)z * vm.sv[1] + (size_t)x * vm.su[1]) * 4, r);
     }
     // d/d plane2[z][y][c] = sum_x g * l2[x][c]: reduce over tx (lane bits 0..2)
     {
@@ -468,14 +468,14 @@ k_dense_l1(dynrf_vm_t vm, int act, float shift, int Gx, int Gy, int Gz, int zchu
         r.x += __shfl_xor_sync(0xffffffffu, r.x, o); r.y += __shfl_xor_sync(0xffffffffu, r.y, o);
         r.z += __shfl_xor_sync(0xffffffffu, r.z, o); r.w += __shfl_xor_sync(0xffffffffu, r.w, o);
       }
-      if (tx == 0 && y < Gy) red_add4g(gp2 + ((size_t)z * Gy + y) * 4, r);
+      if (tx == 0 && y < Gy) red_add4g(gp2 + ((size_t)z * vm.sv[2] + (size_t)y * vm.su[2]) * 4, r);
     }
   }
   const double tot = block_sum_d<kL1Threads>((double)total, red);
   if (threadIdx.x == 0 && tot != 0.0) atomicAdd(sum_out, tot);
   if (!grad) return;
   if (in) {
-    float* p = gp0 + ((size_t)y * Gx + x) * 16;
+    float* p = gp0 + ((size_t)y * vm.sv[0] + (size_t)x * vm.su[0]) * 16;
 #pragma unroll
     for (int c = 0; c < 16; c += 4) red_add4g(p + c, make_float4(gP0[c], gP0[c + 1], gP0[c + 2], gP0[c + 3]));   // z chunks add up
   }
@@ -579,6 +579,7 @@ int dynrf_tv_fused(int n, const float* const* x, float* const* g, const int32_t*
 }
 
 int dynrf_dense_l1(const dynrf_vm_t* vm, int act, float shift, double* sum_out, const dynrf_vm_grad_t* g, void* stream) {
+  if (vm && !dynrf_vm_layout_ok(vm)) return DYNRF_E_UNSUPPORTED;
   if (!vm || !sum_out) return DYNRF_E_ARG;
   if (vm->C[0] != 16 || vm->C[1] != 4 || vm->C[2] != 4) return DYNRF_E_UNSUPPORTED;
   const int Gx = vm->W[0], Gy = vm->H[0], Gz = vm->L[0];

@@ -443,6 +443,7 @@ int dynrf_dyn_sigma_blend_fwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* de
                               const dynrf_layer_t* d1, const dynrf_layer_t* d2, const dynrf_layer_t* b1, const dynrf_layer_t* b2,
                               const float* xyz, const float* xyz_prime, const uint8_t* valid, const float* tfeat, int N, int S,
                               float* sigma, float* blend, void* stream) {
+  if (density && blending && (!dynrf_vm_layout_ok(density) || !dynrf_vm_same_layout(density, blending))) return DYNRF_E_UNSUPPORTED;
   if (!cfg || !xyz || !xyz_prime || !valid || !tfeat || !sigma || !blend || N <= 0 || S <= 0) return DYNRF_E_ARG;
   DYNRF_TRY(check_vm_counts(density, 16, 4, 4));
   DYNRF_TRY(check_vm_counts(blending, 16, 4, 4));
@@ -464,6 +465,7 @@ int dynrf_dyn_app_fwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* app, const
                       const dynrf_layer_t* l2, const dynrf_layer_t* l3, const float* rays, const float* xyz,
                       const float* xyz_prime, const float* tfeat, int N, int S, const int32_t* active_idx,
                       const int32_t* active_count, float* rgb, float* featT, int ldf, void* stream) {
+  if (app && !dynrf_vm_layout_ok(app)) return DYNRF_E_UNSUPPORTED;
   if (!cfg || !rays || !xyz || !xyz_prime || !tfeat || !active_idx || !active_count || !rgb || N <= 0 || S <= 0) return DYNRF_E_ARG;
   if (featT && ldf < ((N * S + kTileM - 1) / kTileM) * kTileM) return DYNRF_E_ARG;
   DYNRF_TRY(check_vm_counts(app, 48, 12, 12));
@@ -483,6 +485,7 @@ int dynrf_dyn_app_fwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* app, const
 int dynrf_static_app_fwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* app, const dynrf_layer_t* basis, const dynrf_layer_t* l1,
                          const dynrf_layer_t* l2, const dynrf_layer_t* l3, int head_mode, const float* rays, const float* xyz, int N,
                          int S, const int32_t* active_idx, const int32_t* active_count, float* rgb, void* stream) {
+  if (app && !dynrf_vm_layout_ok(app)) return DYNRF_E_UNSUPPORTED;
   if (!cfg || !rays || !xyz || !active_idx || !active_count || !rgb || N <= 0 || S <= 0) return DYNRF_E_ARG;
   DYNRF_TRY(check_vm_counts(app, 48, 12, 12));
   DYNRF_TRY(check_layer(basis, 72, 27, 32));

@@ -209,7 +209,7 @@ k_static_sigma_weight(dynrf_field_cfg_t cfg, dynrf_vm_t vm, const float* __restr
         const Tap1 tl = make_tap(xn[l], vm.L[pl], 1);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int c = 0; c < vm.C[pl]; c += 4) {
-          const float4 g = vm_group(vm.plane[pl], vm.line[pl], vm.C[pl], vm.W[pl], tu, tv, tl, c);
+          const float4 g = vm_group(vm.plane[pl], vm.line[pl], vm.C[pl], plane_st(vm, pl), tu, tv, tl, c);
           acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
         }
         feat += (acc.x + acc.y) + (acc.z + acc.w);
@@ -459,6 +459,7 @@ int dynrf_static_sigma_weight_fwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t
                                   const float* xyz, const float* z_vals, const uint8_t* valid, const float* zvec,
                                   float* sigma, float* weight, float* dists, int32_t* active_idx, int32_t* active_count,
                                   float* rgb_zero, void* stream) {
+  if (density && !dynrf_vm_layout_ok(density)) return DYNRF_E_UNSUPPORTED;
   if (!cfg || !density || !rays || !sigma || !weight || !dists || !active_idx || !active_count || N <= 0 || S <= 0)
     return DYNRF_E_ARG;
   if (int e = check_vm(density)) return e;

@@ -179,13 +179,13 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
           const TapF tx = load_tap(taps, si, 0, m), ty = load_tap(taps, si, 1, m), tz = load_tap(taps, si, 2, m);
           {
             float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (act) r = vm_group_f(vapp.plane[0], vapp.line[0], 48, G[0], tx, ty, tz, (c * 6 + prt) * 4);
+            if (act) r = vm_group_f(vapp.plane[0], vapp.line[0], 48, plane_st(vapp, 0), tx, ty, tz, (c * 6 + prt) * 4);
             store_quad(buf, m, prt, r);
           }
           if ((c == 0) == (prt < 2)) {  // c = 0: threads 0,1 take groups 4,5; c = 1: threads 2,3 take groups 10,11
             const int e = c == 0 ? prt : prt - 2;
             float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (act) r = vm_group_f(vapp.plane[0], vapp.line[0], 48, G[0], tx, ty, tz, (c * 6 + 4 + e) * 4);
+            if (act) r = vm_group_f(vapp.plane[0], vapp.line[0], 48, plane_st(vapp, 0), tx, ty, tz, (c * 6 + 4 + e) * 4);
             store_quad(buf, m, 4 + e, r);
           }
         } else {
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
             const bool p1 = qd < 3;
             float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
             if (act)
-              r = vm_group_f(p1 ? vapp.plane[1] : vapp.plane[2], p1 ? vapp.line[1] : vapp.line[2], 12, p1 ? G[0] : G[1],
+              r = vm_group_f(p1 ? vapp.plane[1] : vapp.plane[2], p1 ? vapp.line[1] : vapp.line[2], 12, plane_st(vapp, p1 ? 1 : 2),
                              load_tap(taps, si, p1 ? 0 : 1, m), load_tap(taps, si, 2, m), load_tap(taps, si, p1 ? 1 : 0, m),
                              (p1 ? qd : qd - 3) * 4);
             store_quad(buf, m, qd, r);
@@ -399,6 +399,7 @@ int dynrf_pack_app_fwd(int dynamic, int head, const float* basis_w, const float*
 int dynrf_app_fwd_tc(const dynrf_field_cfg_t* cfg, int dynamic, const dynrf_vm_t* app, const float* wq, const float* cst,
                      const float* rays, const float* xyz, const float* coords, const float* tfeat, int N, int S,
                      const int32_t* active_idx, const int32_t* active_count, float* rgb, float* featT, int ld, void* stream) {
+  if (app && !dynrf_vm_layout_ok(app)) return DYNRF_E_UNSUPPORTED;
   if (!cfg || !app || !wq || !cst || !rays || !xyz || !coords || !active_idx || !active_count || !rgb || N <= 0 || S <= 0) return DYNRF_E_ARG;
   if (dynamic && !tfeat) return DYNRF_E_ARG;
   if (featT && ((ld & 3) || ld < ((N * S + kTileM - 1) / kTileM) * kTileM)) return DYNRF_E_ARG;

@@ -647,6 +647,7 @@ int dynrf_head_bwd_tc(const dynrf_field_cfg_t* cfg, int dynamic, const float* wq
 int dynrf_basis_bwd(const dynrf_field_cfg_t* cfg, int dynamic, const dynrf_vm_t* app, const dynrf_vm_grad_t* gapp, const float* wbB,
                     const float* coords, const float* DFT, int ld, int N, int S, const int32_t* active_idx,
                     const int32_t* active_count, float* gbasis_wt, float* gcoord, void* stream) {
+  if (app && !dynrf_vm_layout_ok(app)) return DYNRF_E_UNSUPPORTED;
   if (!cfg || !app || !gapp || !wbB || !coords || !DFT || !active_idx || !active_count || !gbasis_wt || N <= 0 || S <= 0) return DYNRF_E_ARG;
   if (app->C[0] != 48 || app->C[1] != 12 || app->C[2] != 12) return DYNRF_E_UNSUPPORTED;
   // planes (x,y) (x,z) (y,z) of one grid

@@ -445,7 +445,7 @@ k_dyn_sigma_blend_tc2(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, co
             const float* pp = isbl ? vbl.plane[0] : vden.plane[0];
             const float* ll = isbl ? vbl.line[0] : vden.line[0];
             float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (act) r = vm_group_f(pp, ll, 16, G[0], load_tap(taps, si, 0, m), load_tap(taps, si, 1, m), load_tap(taps, si, 2, m), prt * 4);
+            if (act) r = vm_group_f(pp, ll, 16, plane_st(vden, 0), load_tap(taps, si, 0, m), load_tap(taps, si, 1, m), load_tap(taps, si, 2, m), prt * 4);
             store_quad(buf, m, prt, r);
             if (XT) store_quad_g(XT, ld, xrow + prt * 4, tile * kTileM + m, r);
           }
@@ -455,7 +455,7 @@ k_dyn_sigma_blend_tc2(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, co
             float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
             // plane 1: (u,v,l) = (x,z,y), W = Gx; plane 2: (y,z,x), W = Gy
             if (act)
-              r = vm_group_f(pp, ll, 4, prt == 0 ? G[0] : G[1], load_tap(taps, si, prt == 0 ? 0 : 1, m), load_tap(taps, si, 2, m),
+              r = vm_group_f(pp, ll, 4, plane_st(vden, prt == 0 ? 1 : 2), load_tap(taps, si, prt == 0 ? 0 : 1, m), load_tap(taps, si, 2, m),
                              load_tap(taps, si, prt == 0 ? 1 : 0, m), 0);
             store_quad(buf, m, 4 + prt, r);
             if (XT) store_quad_g(XT, ld, xrow + 16 + prt * 4, tile * kTileM + m, r);
@@ -621,6 +621,7 @@ int dynrf_dyn_sigma_blend_fwd_tc2(const dynrf_field_cfg_t* cfg, const dynrf_vm_t
                                   const float* wq, const float* b1cat, const float* w2cat, const float* b2cat, const float* xyz,
                                   const float* xyz_prime, const uint8_t* valid, const float* tfeat, int N, int S, float* sigma,
                                   float* blend, float* XT, float* HT, int ld, void* stream) {
+  if (density && blending && (!dynrf_vm_layout_ok(density) || !dynrf_vm_same_layout(density, blending))) return DYNRF_E_UNSUPPORTED;
   if (!cfg || !density || !blending || !wq || !b1cat || !w2cat || !b2cat || !xyz || !xyz_prime || !valid || !tfeat || !sigma || !blend ||
       N <= 0 || S <= 0)
     return DYNRF_E_ARG;
@@ -663,6 +664,7 @@ int dynrf_dyn_sigma_blend_fwd_tc(const dynrf_field_cfg_t* cfg, const dynrf_vm_t*
                                  const dynrf_umma_layer_t* d1, const dynrf_layer_t* d2, const dynrf_umma_layer_t* b1,
                                  const dynrf_layer_t* b2, const float* xyz, const float* xyz_prime, const uint8_t* valid,
                                  const float* tfeat, int N, int S, float* sigma, float* blend, void* stream) {
+  if (density && blending && (!dynrf_vm_layout_ok(density) || !dynrf_vm_same_layout(density, blending))) return DYNRF_E_UNSUPPORTED;
   if (!cfg || !density || !blending || !d2 || !b2 || !xyz || !xyz_prime || !valid || !tfeat || !sigma || !blend || N <= 0 || S <= 0)
     return DYNRF_E_ARG;
   DYNRF_TRY(check_ul(d1, 152, 64));

@@ -196,7 +196,7 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
             const float* pp = isbl ? vbl.plane[0] : vden.plane[0];
             const float* ll = isbl ? vbl.line[0] : vden.line[0];
             float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (act) r = vm_group(pp, ll, 16, G[0], load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 1, m, G[1]), load_tap1(taps, si, 2, m, G[2]), prt * 4);
+            if (act) r = vm_group(pp, ll, 16, plane_st(vden, 0), load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 1, m, G[1]), load_tap1(taps, si, 2, m, G[2]), prt * 4);
             store_quad(buf, m, prt, r);
             store_quad_g(a.XT, ld, xrow + prt * 4, i0g + m, r);
           }
@@ -205,7 +205,7 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
             const float* ll = prt == 0 ? (isbl ? vbl.line[1] : vden.line[1]) : (isbl ? vbl.line[2] : vden.line[2]);
             float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
             const int au = prt == 0 ? 0 : 1, al = prt == 0 ? 1 : 0;
-            if (act) r = vm_group(pp, ll, 4, G[au], load_tap1(taps, si, au, m, G[au]), load_tap1(taps, si, 2, m, G[2]), load_tap1(taps, si, al, m, G[al]), 0);
+            if (act) r = vm_group(pp, ll, 4, plane_st(vden, prt == 0 ? 1 : 2), load_tap1(taps, si, au, m, G[au]), load_tap1(taps, si, 2, m, G[2]), load_tap1(taps, si, al, m, G[al]), 0);
             store_quad(buf, m, 4 + prt, r);
             store_quad_g(a.XT, ld, xrow + 16 + prt * 4, i0g + m, r);
           }
@@ -294,7 +294,7 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
               const float* ll = tb ? vbl.line[0] : vden.line[0];
               float* gp = tb ? gbl.plane[0] : gden.plane[0];
               float* gl = tb ? gbl.line[0] : gden.line[0];
-              const float3 r = vm_group_bwd_w(pp, ll, gp, gl, 16, G[0], load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 1, m, G[1]),
+              const float3 r = vm_group_bwd_w(pp, ll, gp, gl, 16, plane_st(vden, 0), load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 1, m, G[1]),
                                                 load_tap1(taps, si, 2, m, G[2]), prt * 4, g4, act, lane);
               g0 += r.x;
               g1 += r.y;
@@ -309,13 +309,13 @@ k_dyn_mlp_bwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, dynrf_v
             float* gp = prt == 0 ? (tb ? gbl.plane[1] : gden.plane[1]) : (tb ? gbl.plane[2] : gden.plane[2]);
             float* gl = prt == 0 ? (tb ? gbl.line[1] : gden.line[1]) : (tb ? gbl.line[2] : gden.line[2]);
             if (prt == 0) {  // plane (x, z), line y
-              const float3 r = vm_group_bwd_w(pp, ll, gp, gl, 4, G[0], load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 2, m, G[2]),
+              const float3 r = vm_group_bwd_w(pp, ll, gp, gl, 4, plane_st(vden, 1), load_tap1(taps, si, 0, m, G[0]), load_tap1(taps, si, 2, m, G[2]),
                                                 load_tap1(taps, si, 1, m, G[1]), 0, g4, act, lane);
               g0 += r.x;
               g2 += r.y;
               g1 += r.z;
             } else {  // plane (y, z), line x
-              const float3 r = vm_group_bwd_w(pp, ll, gp, gl, 4, G[1], load_tap1(taps, si, 1, m, G[1]), load_tap1(taps, si, 2, m, G[2]),
+              const float3 r = vm_group_bwd_w(pp, ll, gp, gl, 4, plane_st(vden, 2), load_tap1(taps, si, 1, m, G[1]), load_tap1(taps, si, 2, m, G[2]),
                                                 load_tap1(taps, si, 0, m, G[0]), 0, g4, act, lane);
               g1 += r.x;
               g2 += r.y;
@@ -413,6 +413,7 @@ int dynrf_dyn_mlp_bwd_tc(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density
                          const float* xyz, const float* xyz_prime, const uint8_t* valid, const float* tfeat, const float* gsigma,
                          const float* gblend, int N, int S, int ld, float* XT, const float* HT_saved, float* DHT, float* gxp,
                          float* gw2, float* gb1, float* gb2, void* stream) {
+  if (density && blending && (!dynrf_vm_layout_ok(density) || !dynrf_vm_same_layout(density, blending))) return DYNRF_E_UNSUPPORTED;
   if (!cfg || !density || !blending || !gdensity || !gblending || !wq || !cst || !xyz || !xyz_prime || !valid || !tfeat || !XT || !DHT ||
       !gxp || !gw2 || !gb1 || !gb2 || N <= 0 || S <= 0 || (ld & 3) || ld < ((N * S + kTileM - 1) / kTileM) * kTileM)
     return DYNRF_E_ARG;

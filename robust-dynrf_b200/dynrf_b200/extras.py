@@ -160,7 +160,8 @@ class _TvFn(torch.autograd.Function):
         xs, gs, Cs, Hs, Ws, ch, cw, counts = [], [], [], [], [], [], [], []
         for t, sc in zip(tensors, scales):
             x = t.detach()
-            if not _is_channel_last(x):
+            hfast = (not _is_channel_last(x)) and ops.is_hfast(x)     # the z planes are stored [W][H][C]
+            if not hfast and not _is_channel_last(x):
                 x = x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
             b, c, h, w = x.shape
             if b != 1:
@@ -168,10 +169,14 @@ class _TvFn(torch.autograd.Function):
             count_h, count_w = c * (h - 1) * w, c * h * (w - 1)
             xs.append(x)
             gs.append(torch.empty_like(x, memory_format=torch.preserve_format) if any_grad else None)
-            Cs.append(c), Hs.append(h), Ws.append(w)
-            ch.append(sc * weight * 2.0 / count_h / b if count_h > 0 else 0.0)
-            cw.append(sc * weight * 2.0 / count_w / b if count_w > 0 else 0.0)
-            counts.append((count_h, count_w, b, sc))
+            kh = sc * weight * 2.0 / count_h / b if count_h > 0 else 0.0
+            kw = sc * weight * 2.0 / count_w / b if count_w > 0 else 0.0
+            Cs.append(c)
+            if hfast:      # the kernel sees the physical [rows = W][cols = H] tensor: its "h" direction is the logical w direction
+                Hs.append(w), Ws.append(h), ch.append(kw), cw.append(kh)
+            else:
+                Hs.append(h), Ws.append(w), ch.append(kh), cw.append(kw)
+            counts.append((count_h, count_w, b, sc, hfast))
         sums = torch.zeros(2 * n, device=dev, dtype=torch.float64)
         xa = (C.c_void_p * n)(*[x.data_ptr() for x in xs])
         ga = (C.c_void_p * n)(*[(g.data_ptr() if g is not None else None) for g in gs])
@@ -181,9 +186,10 @@ class _TvFn(torch.autograd.Function):
                 "dynrf_tv_fused")
         s32 = sums.float()
         total = torch.zeros((), device=dev)
-        for i, (count_h, count_w, b, sc) in enumerate(counts):
+        for i, (count_h, count_w, b, sc, hfast) in enumerate(counts):
+            h_tv, w_tv = (s32[2 * i + 1], s32[2 * i]) if hfast else (s32[2 * i], s32[2 * i + 1])
             # same expression as TVLoss.forward: weight * 2 * (h_tv / count_h + w_tv / count_w) / batch  (0/0 -> NaN for lines)
-            total = total + (weight * 2 * (s32[2 * i] / count_h + s32[2 * i + 1] / count_w) / b) * sc
+            total = total + (weight * 2 * (h_tv / count_h + w_tv / count_w) / b) * sc
         ctx.gs = gs
         return total
 

@@ -52,7 +52,7 @@ def build(verbose: bool = False) -> str:
 
 class VmT(C.Structure):
     _fields_ = [("plane", C.c_void_p * 3), ("line", C.c_void_p * 3), ("C", C.c_int32 * 3), ("H", C.c_int32 * 3),
-                ("W", C.c_int32 * 3), ("L", C.c_int32 * 3)]
+                ("W", C.c_int32 * 3), ("L", C.c_int32 * 3), ("sv", C.c_int32 * 3), ("su", C.c_int32 * 3)]
 
 
 class VmGradT(C.Structure):

@@ -11,6 +11,7 @@ Reference functions replaced (paths relative to the reference checkout):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -55,13 +56,40 @@ def to_channel_last_(p: torch.Tensor) -> None:
             p.data = p.data.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
 
 
+def is_hfast(p: torch.Tensor) -> bool:
+    """True if a (1,C,H,W) tensor is physically [W][H][C] (H fastest among the two texel dimensions)."""
+    _, c, h, w = p.shape
+    s = p.stride()
+    return (c == 1 or s[1] == 1) and (h == 1 or s[2] == c) and (w == 1 or s[3] == h * c)
+
+
+# "zfast" (default) or "xfast" (every plane [H][W][C], the round-1 layout; kept selectable for A/B measurements)
+PLANE_LAYOUT = os.environ.get("DYNRF_PLANE_LAYOUT", "zfast")
+
+
+def to_plane_layout_(p: torch.Tensor, plane_index: int) -> None:
+    """Native layout of VM plane `plane_index` (logical shape (1,C,H,W) unchanged):
+      plane 0 (x, y)           : [H][W][C]  -- the samples of a ray share their (x, y) texel, nothing to coalesce;
+      planes 1, 2 (x|y, z = H) : [W][H][C]  -- z fastest: consecutive samples of a ray (= consecutive lanes of a warp) advance
+                                  mostly in z, so their taps fall into a few contiguous 128-byte lines instead of one row each."""
+    if plane_index == 0 or PLANE_LAYOUT == "xfast":
+        to_channel_last_(p)
+    elif not is_hfast(p):
+        with torch.no_grad():
+            p.data = p.data.permute(0, 3, 2, 1).contiguous().permute(0, 3, 2, 1)
+
+
 _VM_CACHE: Dict[tuple, "L.VmT"] = {}
 
 
+def _vm_key(planes, lines):
+    return tuple((t.data_ptr(), t.shape[2], t.shape[3], t.stride(1), t.stride(2), t.stride(3)) for t in (*planes, *lines))
+
+
 def vm_struct(planes: Sequence[torch.Tensor], lines: Sequence[torch.Tensor]) -> L.VmT:
-    """dynrf_vm_t for a plane/line set; cached on (data_ptr, shape) of the six tensors (pointers only change when a
+    """dynrf_vm_t for a plane/line set; cached on (data_ptr, shape, strides) of the six tensors (pointers only change when a
     parameter is replaced, e.g. by upsample_volume_grid; values may change in place)."""
-    key = tuple((t.data_ptr(), t.shape[2], t.shape[3], t.stride(1)) for t in (*planes, *lines))
+    key = _vm_key(planes, lines)
     hit = _VM_CACHE.get(key)
     if hit is not None:
         return hit
@@ -69,21 +97,21 @@ def vm_struct(planes: Sequence[torch.Tensor], lines: Sequence[torch.Tensor]) -> 
         _VM_CACHE.clear()
     vm = _vm_struct_build(planes, lines)
     # re-key after a possible in-place layout conversion moved the storage
-    key = tuple((t.data_ptr(), t.shape[2], t.shape[3], t.stride(1)) for t in (*planes, *lines))
-    _VM_CACHE[key] = vm
+    _VM_CACHE[_vm_key(planes, lines)] = vm
     return vm
 
 
 def _vm_struct_build(planes: Sequence[torch.Tensor], lines: Sequence[torch.Tensor]) -> L.VmT:
     vm = L.VmT()
     for i in range(3):
-        to_channel_last_(planes[i])
+        to_plane_layout_(planes[i], i)
         to_channel_last_(lines[i])
         _, c, h, w = planes[i].shape
         vm.plane[i] = planes[i].data_ptr()
         vm.line[i] = lines[i].data_ptr()
         vm.C[i], vm.H[i], vm.W[i] = c, h, w
         vm.L[i] = lines[i].shape[2]
+        vm.sv[i], vm.su[i] = (1, h) if (i > 0 and PLANE_LAYOUT != "xfast") else (w, 1)
         if lines[i].shape[1] != c:
             raise ValueError("plane/line component counts differ")
     return vm

@@ -49,7 +49,7 @@ class _VMMixin:
                                                    align_corners=True))
             lines[i] = nn.Parameter(F.interpolate(lines[i].data, size=(res_target[v], 1), mode="bilinear",
                                                   align_corners=True))
-            _ops.to_channel_last_(planes[i])
+            _ops.to_plane_layout_(planes[i], i)
             _ops.to_channel_last_(lines[i])
         return planes, lines
 

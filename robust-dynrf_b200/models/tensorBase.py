@@ -4,7 +4,7 @@ Same class / function names, constructor kwargs, attribute names and state_dict 
 models/tensorBase.py in facebookresearch/robust-dynrf, but `TensorBase.forward` and the
 samplers run the sm_100a kernels of libdynrf_b200.so instead of the grid_sample / cumprod /
 Linear chain.  Planes and lines keep their logical (1,C,H,W)/(1,C,L,1) shapes and are stored
-channel-last so one bilinear tap is one contiguous 16..192-byte read.
+channel-last (one bilinear tap is one contiguous 16..192-byte read), the two z planes with z as the fastest texel dimension.
 
 Out of scope here (never reached by train.py): AlphaGridMask, updateAlphaMask,
 filtering_rays, shrink, compute_alpha, the dead shading modes (MLP_PE, MLP, MLP_Fea_woView, RGB).
@@ -149,7 +149,9 @@ class TensorBase(nn.Module):
             planes.append(nn.Parameter(scale * torch.randn((1, c, int(gridSize[m1]), int(gridSize[m0])))))
             lines.append(nn.Parameter(scale * torch.randn((1, c, int(gridSize[v]), 1))))
         planes, lines = nn.ParameterList(planes).to(device), nn.ParameterList(lines).to(device)
-        for p in list(planes) + list(lines):
+        for i, p in enumerate(planes):
+            _ops.to_plane_layout_(p, i)     # plane 0 [H][W][C]; planes 1, 2 [W][H][C] (z fastest), see ops.to_plane_layout_
+        for p in lines:
             _ops.to_channel_last_(p)
         return planes, lines
 
