@@ -85,7 +85,8 @@ __device__ __forceinline__ void sincos4(float x, float base, float4& s, float4& 
 
 // position/time operand rows, unit u of 14 (see K order above); writes into the chunk buffer that holds its quads
 // gT != nullptr: additionally stream the quads feature-major to gT (rows = this chunk's rows, row stride ld) at column gcol
-__device__ __forceinline__ void produce_pos_unit(int u, const TileScratch<kTileM>& scr, const float* __restrict__ tfeat, int m,
+template <class Scr>
+__device__ __forceinline__ void produce_pos_unit(int u, const Scr& scr, const float* __restrict__ tfeat, int m,
                                                  float* __restrict__ buf, float* __restrict__ gT = nullptr, int ld = 0, int gcol = 0) {
 #define DYNRF_PUT(q_, v_)                                        \
   do {                                                           \

@@ -63,8 +63,60 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
   for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
 }
 
-constexpr size_t kAfSmem = (size_t)(3 * kOpFloats + 2 * kWSlotFloats + kAfCst + 4 * 3 * kTileM) * sizeof(float) + sizeof(TapsSmem) +
-                           sizeof(TileScratch<kTileM>) + 128;
+// ---- two tiles in flight per CTA --------------------------------------------------------------------------------------------
+// A tile is a chain of dependent stages (gathers -> basis GEMM -> head input -> L1 -> L2 -> output layer).  With one tile per CTA
+// the producer warps sit at an mbarrier while the tensor core finishes each GEMM group (29 % of the stall samples of the
+// one-tile kernel: 12.7 % before the L1 read-back, 12.0 % before the L2 read-back, 3.9 % before the basis read-back) and the
+// tensor core idles while they gather.  The CTA therefore keeps TWO tiles in flight in a software pipeline skewed by half a
+// tile: iteration k starts tile Y = k (context k & 1) and finishes tile X = k - 1 (the other context), in the order
+//
+//     S0(Y) scratch + taps | S1a(Y) basis operand chunks | S3(X) L1 read-back -> L2 operand chunks |
+//     S1b(Y) position/time chunks (dynamic head) | S2(Y) basis read-back -> L1 operand chunks | S4(X) L2 read-back -> rgb
+//
+// so that every read-back of a GEMM group is separated from the production of its last operand chunk by a long SIMT stage of the
+// OTHER tile: L1(X) runs on the tensor core under S0 + S1a(Y), L2(X) under S1b + S2(Y), basis(Y) under S3(X).  The operand ring
+// and the weight slots are shared; the ring order is the static sequence Y.basis, X.L2, Y.(rest of L1), which the tensor-core
+// warp follows with the same generator (AppSeq).  Every (context, GEMM group) has its own completion mbarrier (tcgen05.commit
+// after the group's last chunk, one phase per tile of that context): a wait on an operand-buffer barrier several chunks back
+// would alias with a later phase of that barrier.
+//
+// TMEM columns of context s (base 160 s): [0,32) basis output | [32,160) L1 pre-activation, later L2 pre-activation (every warp
+// has read its L1 columns before it arrives on the first L2 chunk, and that chunk's MMA needs all 16 arrivals).
+struct FwdScratch {
+  float xn[3][kTileM];  // normalize(xyz)
+  float xq[3][kTileM];  // normalize(lookup coordinates)
+  float xu[3][kTileM];  // view direction
+  int ray[kTileM], idx[kTileM], on[kTileM];
+};
+
+// position in the CTA's chunk sequence: iteration k, phase ph (0: Y.basis, 1: X.L2, 2: Y.rest of L1), index i inside the phase
+template <bool DYN>
+struct AppSeq {
+  using AF = AppFwd<DYN>;
+  int k, ph, i, T;  // T = number of tiles of this CTA; iterations k = 0..T
+  __device__ __forceinline__ int len() const {
+    if (ph == 0) return k < T ? AF::kNB : 0;
+    if (ph == 1) return k >= 1 ? 4 : 0;
+    return k < T ? AF::kNL1 : 0;
+  }
+  __device__ __forceinline__ void norm() {
+    while (k <= T && i >= len()) {
+      i = 0;
+      if (++ph == 3) {
+        ph = 0;
+        ++k;
+      }
+    }
+  }
+  __device__ __forceinline__ bool valid() const { return k <= T; }
+  __device__ __forceinline__ int j() const { return ph == 0 ? i : (ph == 1 ? AF::kNB + AF::kNL1 + i : AF::kNB + i); }
+  __device__ __forceinline__ int s() const { return (ph == 1 ? k - 1 : k) & 1; }
+};
+
+constexpr int kAfCtxCols = 160;
+constexpr size_t kAfSmem = (size_t)(3 * kOpFloats + 2 * kWSlotFloats + kAfCst + 2 * 4 * 3 * kTileM) * sizeof(float) + 2 * sizeof(TapsSmem) +
+                           2 * sizeof(FwdScratch) + 256;
+static_assert(kAfSmem <= 232448, "k_app_fwd_tc shared memory");
 
 template <bool DYN>
 __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t cfg, dynrf_vm_t vapp, AppFwdArgs a) {
@@ -73,18 +125,20 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
   float* abuf = smem;
   float* wbuf = abuf + 3 * kOpFloats;
   float* cst = wbuf + 2 * kWSlotFloats;
-  float* part = cst + kAfCst;  // [4][3][128]
-  TapsSmem& taps = *reinterpret_cast<TapsSmem*>(part + 4 * 3 * kTileM);
-  TileScratch<kTileM>& scr = *reinterpret_cast<TileScratch<kTileM>*>(reinterpret_cast<uint8_t*>(&taps) + sizeof(TapsSmem));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(&scr) + sizeof(TileScratch<kTileM>));
-  uint64_t* bar_free = bars;
-  uint64_t* bar_w = bars + 3;
-  uint64_t* bar_full = bars + 5;
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* part0 = cst + kAfCst;  // [2][4][3][128]
+  TapsSmem* tapsv = reinterpret_cast<TapsSmem*>(part0 + 2 * 4 * 3 * kTileM);
+  FwdScratch* scrv = reinterpret_cast<FwdScratch*>(tapsv + 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scrv + 2);
+  uint64_t* bar_free = bars;        // [3]
+  uint64_t* bar_w = bars + 3;       // [2]
+  uint64_t* bar_full = bars + 5;    // [3]
+  uint64_t* bar_stage = bars + 8;   // [2 contexts][3 GEMM groups: basis, L1, L2]
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 14);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) umma::mbar_init(&bars[i], 1);
     for (int i = 0; i < 3; ++i) umma::mbar_init(&bar_full[i], kProdThreads / 32);
+    for (int i = 0; i < 6; ++i) umma::mbar_init(&bar_stage[i], 1);
     umma::fence_mbar_init();
   }
   for (int i = tid; i < kAfCst; i += kTc3Threads) cst[i] = __ldg(a.cst + i);
@@ -96,7 +150,6 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
   const int count = *a.active_count;
   const int ntiles = (count + kTileM - 1) / kTileM;
   const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const uint32_t total_chunks = (uint32_t)my_tiles * AF::kChunks;
   const float* b1 = cst;
   const float* b2 = cst + 128;
   const float* W3t = cst + 256;
@@ -104,19 +157,25 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
   const float* b3 = cst + 649;
 
   if (warp == kProdThreads / 32) {
-    if (lane == 0 && total_chunks > 0) {
-      ring_prefetch_w(ring, 0, a.wq + AF::woff(0), 2u * AF::n(0) * AF::rows(0) * 4u);
-      for (uint32_t c = 0; c < total_chunks; ++c) {
-        const int j = (int)(c % AF::kChunks);
+    // ===================== tensor-core warp: follows the chunk sequence =====================
+    if (lane == 0 && my_tiles > 0) {
+      AppSeq<DYN> sq{0, 0, 0, my_tiles};
+      sq.norm();
+      ring_prefetch_w(ring, 0, a.wq + AF::woff(sq.j()), 2u * AF::n(sq.j()) * AF::rows(sq.j()) * 4u);
+      for (uint32_t c = 0; sq.valid(); ++c) {
+        const int j = sq.j(), s = sq.s();
         ring.chunk = c;
         umma::mbar_wait(&bar_full[c % 3], (c / 3) & 1);
-        if (j < AF::kNB) ring_issue<32>(ring, 24, 0u, j == 0);
-        else if (j < AF::kNB + AF::kNL1) ring_issue<128>(ring, AF::rows(j), 32u, j == AF::kNB);
-        else ring_issue<128>(ring, 32, 160u, j == AF::kNB + AF::kNL1);
-        if (c + 1 < total_chunks) {
-          const int nj = (j + 1) % AF::kChunks;
-          ring_prefetch_w(ring, c + 1, a.wq + AF::woff(nj), 2u * AF::n(nj) * AF::rows(nj) * 4u);
-        }
+        const uint32_t col = (uint32_t)(s * kAfCtxCols);
+        if (j < AF::kNB) ring_issue<32>(ring, 24, col, j == 0);
+        else if (j < AF::kNB + AF::kNL1) ring_issue<128>(ring, AF::rows(j), col + 32u, j == AF::kNB);
+        else ring_issue<128>(ring, 32, col + 32u, j == AF::kNB + AF::kNL1);
+        if (j == AF::kNB - 1) umma::commit(&bar_stage[s * 3 + 0]);
+        else if (j == AF::kNB + AF::kNL1 - 1) umma::commit(&bar_stage[s * 3 + 1]);
+        else if (j == AF::kChunks - 1) umma::commit(&bar_stage[s * 3 + 2]);
+        ++sq.i;
+        sq.norm();
+        if (sq.valid()) ring_prefetch_w(ring, c + 1, a.wq + AF::woff(sq.j()), 2u * AF::n(sq.j()) * AF::rows(sq.j()) * 4u);
       }
     }
     __syncwarp();
@@ -127,105 +186,131 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
     const AabbNorm nb = make_norm(cfg);
     const int G[3] = {vapp.W[0], vapp.H[0], vapp.L[0]};
     const int ld = a.ld;
-
-    auto wait_chunk = [&](uint32_t c) {
-      umma::mbar_wait_backoff(&bar_free[c % 3], (c / 3) & 1);
-      umma::fence_after_sync();
-    };
     auto arrive = [&]() {
+      umma::fence_before_sync();   // orders this warp's tcgen05.ld before the MMAs that follow the arrival
       umma::fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[ring.chunk % 3]);
       ring.chunk++;
     };
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int jg0 = tile * kTileM;
-      if (tid < kTileM) {
-        const int jg = jg0 + tid;
-        const bool in = jg < count;
-        const int i = in ? __ldg(a.active_idx + jg) : 0;
-        scr.idx[tid] = i;
-        scr.ray[tid] = in ? i / a.S : -1;
-        scr.on[tid] = in ? 1 : 0;
-        float vd[3] = {0.f, 0.f, 0.f};
-        if (in) ray_viewdir(a.rays, i / a.S, vd);
+#pragma unroll 1
+    for (int k = 0; k <= my_tiles; ++k) {
+      const bool hasY = k < my_tiles, hasX = k >= 1;
+      const int sy = k & 1, sx = (k - 1) & 1;
+      const uint32_t pary = (uint32_t)((k >> 1) & 1), parx = (uint32_t)(((k - 1) >> 1) & 1);
+      const int jgY = ((int)blockIdx.x + k * (int)gridDim.x) * kTileM;
+      FwdScratch& scrY = scrv[sy];
+      FwdScratch& scrX = scrv[sx];
+      const TapsSmem& tapsY = tapsv[sy];
+      const uint32_t tcolY = ring.tmem + (uint32_t)(sy * kAfCtxCols), tcolX = ring.tmem + (uint32_t)(sx * kAfCtxCols);
+      if (hasY) {
+        // ---- S0(Y): per-sample scratch, taps
+        if (tid < kTileM) {
+          const int jg = jgY + tid;
+          const bool in = jg < count;
+          const int i = in ? __ldg(a.active_idx + jg) : 0;
+          scrY.idx[tid] = i;
+          scrY.ray[tid] = in ? i / a.S : -1;
+          scrY.on[tid] = in ? 1 : 0;
+          float vd[3] = {0.f, 0.f, 0.f};
+          if (in) ray_viewdir(a.rays, i / a.S, vd);
 #pragma unroll
-        for (int ax = 0; ax < 3; ++ax) {
-          const float x = in ? __ldg(a.xyz + (size_t)i * 3 + ax) : 0.f;
-          const float xc = in ? __ldg(a.coords + (size_t)i * 3 + ax) : 0.f;
-          scr.xn[ax][tid] = in ? norm_coord(x, nb.mn[ax], nb.inv[ax]) : 0.f;
-          scr.xq[ax][tid] = norm_coord(xc, nb.mn[ax], nb.inv[ax]);
-          scr.xu[ax][tid] = vd[ax];
-        }
-      }
-      prod_bar();
-      for (int item = tid; item < AF::kNS * 3 * kTileM; item += kProdThreads) {
-        const int mm = item & (kTileM - 1), t = item >> 7;
-        const int si = t / 3, ax = t % 3;
-        const Tap1 tp = make_tap(scr.xq[ax][mm], ax == 0 ? G[0] : (ax == 1 ? G[1] : G[2]), 1 << si);
-        taps.t[t][mm] = make_int4(tp.i0, tp.i1, __float_as_int(tp.w0), __float_as_int(tp.w1));
-      }
-      prod_bar();
-      const bool act = scr.on[m] != 0;
-      const uint32_t base = ring.chunk;
-      // ---- basis operand chunks: (stride si, third c): c = 0,1 halves of the 48-channel xy plane; c = 2 the two 12-channel planes
-#pragma unroll 1
-      for (int j = 0; j < AF::kNB; ++j) {
-        ring_wait_free(ring);
-        float* buf = ring_abuf(ring);
-        const int si = j / 3, c = j % 3;
-        if (c < 2) {
-          const TapF tx = load_tap(taps, si, 0, m), ty = load_tap(taps, si, 1, m), tz = load_tap(taps, si, 2, m);
-          {
-            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (act) r = vm_group_f(vapp.plane[0], vapp.line[0], 48, plane_st(vapp, 0), tx, ty, tz, (c * 6 + prt) * 4);
-            store_quad(buf, m, prt, r);
-          }
-          if ((c == 0) == (prt < 2)) {  // c = 0: threads 0,1 take groups 4,5; c = 1: threads 2,3 take groups 10,11
-            const int e = c == 0 ? prt : prt - 2;
-            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (act) r = vm_group_f(vapp.plane[0], vapp.line[0], 48, plane_st(vapp, 0), tx, ty, tz, (c * 6 + 4 + e) * 4);
-            store_quad(buf, m, 4 + e, r);
-          }
-        } else {
-          // quads 0..2: plane 1 (x,z | line y) groups 0..2; quads 3..5: plane 2 (y,z | line x) groups 0..2
-          for (int qd = prt; qd < 6; qd += 4) {
-            const bool p1 = qd < 3;
-            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (act)
-              r = vm_group_f(p1 ? vapp.plane[1] : vapp.plane[2], p1 ? vapp.line[1] : vapp.line[2], 12, plane_st(vapp, p1 ? 1 : 2),
-                             load_tap(taps, si, p1 ? 0 : 1, m), load_tap(taps, si, 2, m), load_tap(taps, si, p1 ? 1 : 0, m),
-                             (p1 ? qd : qd - 3) * 4);
-            store_quad(buf, m, qd, r);
+          for (int ax = 0; ax < 3; ++ax) {
+            const float x = in ? __ldg(a.xyz + (size_t)i * 3 + ax) : 0.f;
+            const float xc = in ? __ldg(a.coords + (size_t)i * 3 + ax) : 0.f;
+            scrY.xn[ax][tid] = in ? norm_coord(x, nb.mn[ax], nb.inv[ax]) : 0.f;
+            scrY.xq[ax][tid] = norm_coord(xc, nb.mn[ax], nb.inv[ax]);
+            scrY.xu[ax][tid] = vd[ax];
           }
         }
-        arrive();
-      }
-      if (DYN) {
+        prod_bar();
+        for (int item = tid; item < AF::kNS * 3 * kTileM; item += kProdThreads) {
+          const int mm = item & (kTileM - 1), t = item >> 7;
+          const int si = t / 3, ax = t % 3;
+          const Tap1 tp = make_tap(scrY.xq[ax][mm], ax == 0 ? G[0] : (ax == 1 ? G[1] : G[2]), 1 << si);
+          tapsv[sy].t[t][mm] = make_int4(tp.i0, tp.i1, __float_as_int(tp.w0), __float_as_int(tp.w1));
+        }
+        prod_bar();
+        // ---- S1a(Y): basis operand chunks (stride si, third c): c = 0,1 halves of the 48-channel xy plane; c = 2 the two
+        //      12-channel planes
+        const bool act = scrY.on[m] != 0;
 #pragma unroll 1
-        for (int j = 0; j < 3; ++j) {
+        for (int j = 0; j < AF::kNB; ++j) {
           ring_wait_free(ring);
           float* buf = ring_abuf(ring);
-          const int u0 = j * 5, nu = (j == 2) ? 4 : 5;
-          for (int u = prt; u < nu; u += 4) produce_pos_unit(u0 + u, scr, a.tfeat, m, buf);
+          const int si = j / 3, c = j % 3;
+          if (c < 2) {
+            const TapF tx = load_tap(tapsY, si, 0, m), ty = load_tap(tapsY, si, 1, m), tz = load_tap(tapsY, si, 2, m);
+            {
+              float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (act) r = vm_group_f(vapp.plane[0], vapp.line[0], 48, plane_st(vapp, 0), tx, ty, tz, (c * 6 + prt) * 4);
+              store_quad(buf, m, prt, r);
+            }
+            if ((c == 0) == (prt < 2)) {  // c = 0: threads 0,1 take groups 4,5; c = 1: threads 2,3 take groups 10,11
+              const int e = c == 0 ? prt : prt - 2;
+              float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (act) r = vm_group_f(vapp.plane[0], vapp.line[0], 48, plane_st(vapp, 0), tx, ty, tz, (c * 6 + 4 + e) * 4);
+              store_quad(buf, m, 4 + e, r);
+            }
+          } else {
+            // quads 0..2: plane 1 (x,z | line y) groups 0..2; quads 3..5: plane 2 (y,z | line x) groups 0..2
+            for (int qd = prt; qd < 6; qd += 4) {
+              const bool p1 = qd < 3;
+              float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (act)
+                r = vm_group_f(p1 ? vapp.plane[1] : vapp.plane[2], p1 ? vapp.line[1] : vapp.line[2], 12, plane_st(vapp, p1 ? 1 : 2),
+                               load_tap(tapsY, si, p1 ? 0 : 1, m), load_tap(tapsY, si, 2, m), load_tap(tapsY, si, p1 ? 1 : 0, m),
+                               (p1 ? qd : qd - 3) * 4);
+              store_quad(buf, m, qd, r);
+            }
+          }
           arrive();
         }
       }
-      // ---- epilogue A: basis output (27 features) -> head input operand
-      // wait on the most recently produced chunk (for the dynamic head: the last position chunk, which shares its operand buffer
-      // with the last basis chunk): tcgen05 operations retire in order, so this also covers the basis GEMM, and a wait on an
-      // older chunk of the same buffer could alias with the next phase of its barrier
-      wait_chunk(base + AF::kNB - 1 + (DYN ? 3 : 0));
-      {
+      if (hasX) {
+        // ---- S3(X): h1 = relu(acc1 + b1) -> L2 operand chunk cb
+        umma::mbar_wait_backoff(&bar_stage[sx * 3 + 1], parx);
+        umma::fence_after_sync();
+        float r[32];
+        umma::tmem_ld32(tcolX + ((uint32_t)(q * 32) << 16) + 32 + cb * 32, r);
+        const bool on = scrX.on[em] != 0;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) r[jj] = on ? fmaxf(r[jj] + b1[cb * 32 + jj], 0.f) : 0.f;
+#pragma unroll 1
+        for (int c4 = 0; c4 < 4; ++c4) {
+          ring_wait_free(ring);
+          if (c4 == cb) {
+            float* buf = ring_abuf(ring);
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) store_quad(buf, em, qq, make_float4(r[qq * 4], r[qq * 4 + 1], r[qq * 4 + 2], r[qq * 4 + 3]));
+          }
+          arrive();
+        }
+      }
+      if (hasY) {
+        // ---- S1b(Y): the three position/time chunks of the dynamic head's first layer
+        if (DYN) {
+#pragma unroll 1
+          for (int j = 0; j < 3; ++j) {
+            ring_wait_free(ring);
+            float* buf = ring_abuf(ring);
+            const int u0 = j * 5, nu = (j == 2) ? 4 : 5;
+            for (int u = prt; u < nu; u += 4) produce_pos_unit(u0 + u, scrY, a.tfeat, m, buf);
+            arrive();
+          }
+        }
+        // ---- S2(Y): basis output (27 features) -> head input operand
+        umma::mbar_wait_backoff(&bar_stage[sy * 3 + 0], pary);
+        umma::fence_after_sync();
         float f[8];
-        tmem_ld8(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 8, f);
-        const bool on = scr.on[em] != 0;
+        tmem_ld8(tcolY + ((uint32_t)(q * 32) << 16) + cb * 8, f);
+        const bool on = scrY.on[em] != 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = on ? f[i] : 0.f;
         if (a.featT) {
-          store_quad_g(a.featT, ld, cb * 8, jg0 + em, make_float4(f[0], f[1], f[2], f[3]));
-          store_quad_g(a.featT, ld, cb * 8 + 4, jg0 + em, make_float4(f[4], f[5], f[6], f[7]));
+          store_quad_g(a.featT, ld, cb * 8, jgY + em, make_float4(f[0], f[1], f[2], f[3]));
+          store_quad_g(a.featT, ld, cb * 8 + 4, jgY + em, make_float4(f[4], f[5], f[6], f[7]));
         }
         if (!DYN) {
 #pragma unroll 1
@@ -251,9 +336,9 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
             arrive();
           }
           if (cb == 3) {  // rows 27..29 of the feature chunk carry the view direction (zero weights for the time-embedding head)
-            f[3] = scr.xu[0][em];
-            f[4] = scr.xu[1][em];
-            f[5] = scr.xu[2][em];
+            f[3] = scrY.xu[0][em];
+            f[4] = scrY.xu[1][em];
+            f[5] = scrY.xu[2][em];
           }
         }
         ring_wait_free(ring);
@@ -264,55 +349,40 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
         }
         arrive();
       }
-      // ---- epilogue B: h1 = relu(acc1 + b1) -> L2 operand chunk cb
-      wait_chunk(base + AF::kNB + AF::kNL1 - 1);
-      {
-        float r[32];
-        umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + 32 + cb * 32, r);
-        const bool on = scr.on[em] != 0;
+      if (hasX) {
+        // ---- S4(X): h2 = relu(acc2 + b2); 3-wide output layer (+ late view direction); sigmoid
+        float* part = part0 + sx * (4 * 3 * kTileM);
+        umma::mbar_wait_backoff(&bar_stage[sx * 3 + 2], parx);
+        umma::fence_after_sync();
+        {
+          float h2[32];
+          umma::tmem_ld32(tcolX + ((uint32_t)(q * 32) << 16) + 32 + cb * 32, h2);
+          float po[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) r[jj] = on ? fmaxf(r[jj] + b1[cb * 32 + jj], 0.f) : 0.f;
-#pragma unroll 1
-        for (int c4 = 0; c4 < 4; ++c4) {
-          ring_wait_free(ring);
-          if (c4 == cb) {
-            float* buf = ring_abuf(ring);
-#pragma unroll
-            for (int qq = 0; qq < 8; ++qq) store_quad(buf, em, qq, make_float4(r[qq * 4], r[qq * 4 + 1], r[qq * 4 + 2], r[qq * 4 + 3]));
+          for (int jj = 0; jj < 32; ++jj) {
+            const int n = cb * 32 + jj;
+            const float h = fmaxf(h2[jj] + b2[n], 0.f);
+            po[0] = fmaf(h, W3t[n * 3 + 0], po[0]);
+            po[1] = fmaf(h, W3t[n * 3 + 1], po[1]);
+            po[2] = fmaf(h, W3t[n * 3 + 2], po[2]);
           }
-          arrive();
-        }
-      }
-      // ---- epilogue C: h2 = relu(acc2 + b2); 3-wide output layer (+ late view direction); sigmoid
-      wait_chunk(base + AF::kChunks - 1);
-      {
-        float h2[32];
-        umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + 160 + cb * 32, h2);
-        float po[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const int n = cb * 32 + jj;
-          const float h = fmaxf(h2[jj] + b2[n], 0.f);
-          po[0] = fmaf(h, W3t[n * 3 + 0], po[0]);
-          po[1] = fmaf(h, W3t[n * 3 + 1], po[1]);
-          po[2] = fmaf(h, W3t[n * 3 + 2], po[2]);
+          for (int c = 0; c < 3; ++c) part[(cb * 3 + c) * kTileM + em] = po[c];
         }
+        umma::fence_before_sync();
+        prod_bar();
+        if (tid < 3 * kTileM) {
+          const int c = tid >> 7, mm = tid & (kTileM - 1);
+          if (scrX.on[mm]) {
+            float o = b3[c] + part[(0 * 3 + c) * kTileM + mm] + part[(1 * 3 + c) * kTileM + mm] + part[(2 * 3 + c) * kTileM + mm] +
+                      part[(3 * 3 + c) * kTileM + mm];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) part[(cb * 3 + c) * kTileM + em] = po[c];
-      }
-      umma::fence_before_sync();
-      prod_bar();
-      if (tid < 3 * kTileM) {
-        const int c = tid >> 7, mm = tid & (kTileM - 1);
-        if (scr.on[mm]) {
-          float o = b3[c] + part[(0 * 3 + c) * kTileM + mm] + part[(1 * 3 + c) * kTileM + mm] + part[(2 * 3 + c) * kTileM + mm] +
-                    part[(3 * 3 + c) * kTileM + mm];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) o = fmaf(scr.xu[k][mm], W3v[k * 3 + c], o);
-          a.rgb[(size_t)scr.idx[mm] * 3 + c] = sigmoidf_(o);
+            for (int kk = 0; kk < 3; ++kk) o = fmaf(scrX.xu[kk][mm], W3v[kk * 3 + c], o);
+            a.rgb[(size_t)scrX.idx[mm] * 3 + c] = sigmoidf_(o);
+          }
         }
+        prod_bar();
       }
-      prod_bar();
     }
   }
   umma::fence_before_sync();

@@ -78,8 +78,69 @@ struct HeadBwdArgs {
 // 16-17 chunks of a tile are consumed back to back: with one chunk of weight look-ahead the kernel ran at the weight latency.
 // Three weight slots (two chunks of look-ahead) and two operand buffers fit the same shared memory.
 constexpr uint32_t kHbBufs = 2, kHbSlots = 3;
-constexpr size_t kHbSmem = (size_t)(kHbBufs * kOpFloats + kHbSlots * kHbWSlot + kHbCst + 4 * 3 * kTileM + 3 * kTileM) * sizeof(float) +
-                           sizeof(TileScratch<kTileM>) + 128;
+
+// ---- two tiles in flight per CTA --------------------------------------------------------------------------------------------
+// A tile is a chain of four dependent GEMM groups (L1 -> L2 -> dH1 -> dX) with an epilogue between each pair; with one tile per
+// CTA the 16 producer warps spent 32 % of their stall samples at the group-completion mbarriers and 21 % at the barriers behind
+// them, while the tensor core idled during every epilogue.  The CTA therefore runs TWO tiles (contexts A, B; tiles dealt
+// alternately) through the five stages  S (scratch + L1 operand), E1, E2, E3, E4  in strict alternation, B half a tile behind A:
+//     S(A) . E1(A) . E2(A) S(B) E3(A) E1(B) E4(A) E2(B) S(A') E3(B) E1(A') E4(B) E2(A') S(B') ...
+// so that between the production of a group's last operand chunk and the read-back of its accumulator the warps always run one
+// stage of the other tile.  Ring, weight slots and the tensor-core warp are shared; the ring order of the chunks follows from the
+// same generator (HeadStageSeq) on both sides.  Every (context, group) has its own completion mbarrier (one phase per tile).
+//
+// TMEM columns of context s (base 256 s): acc1 [0,128) L1 pre-activation | acc2 [128,256) L2 pre-activation, then acc3 = dH1
+// before the ReLU mask (every warp has read acc2 before it arrives on the first dH1-group chunk) | acc4 = dX over acc1 (and, for
+// the static head's N = 160, the first 32 columns of acc3): all reads of acc1 / acc3 precede the barrier in E3.
+struct BwdScratch {
+  float xn[3][kTileM];  // normalize(xyz)
+  float xu[3][kTileM];  // view direction
+  int ray[kTileM], idx[kTileM], on[kTileM];
+};
+
+struct HeadStageSeq {
+  int T, step, st0, st1, tl0, tl1;   // scalars (no indexed arrays: they would live in local memory)
+  int ctx, stage, tile;   // the stage to execute now: context, stage 0..4, tile ordinal (of this CTA) it belongs to
+  __device__ __forceinline__ void init(int T_) {
+    T = T_;
+    step = -1;
+    st0 = st1 = 0;
+    tl0 = 0;
+    tl1 = 1;
+  }
+  // advance to the next executed stage; false when every tile of the CTA is finished
+  __device__ __forceinline__ bool next() {
+    for (;;) {
+      if (tl0 >= T && tl1 >= T) return false;
+      ++step;
+      const int c = step & 1;
+      if (c == 1 && step < 5) continue;   // context B starts two and a half stages behind A
+      if ((c ? tl1 : tl0) >= T) continue;
+      ctx = c;
+      if (c) {
+        stage = st1;
+        tile = tl1;
+        if (++st1 == 5) {
+          st1 = 0;
+          tl1 += 2;
+        }
+      } else {
+        stage = st0;
+        tile = tl0;
+        if (++st0 == 5) {
+          st0 = 0;
+          tl0 += 2;
+        }
+      }
+      return true;
+    }
+  }
+};
+
+constexpr int kHbCtxCols = 256;
+constexpr size_t kHbSmem = (size_t)(kHbBufs * kOpFloats + kHbSlots * kHbWSlot + kHbCst + 2 * (4 * 3 * kTileM + 3 * kTileM)) * sizeof(float) +
+                           2 * sizeof(BwdScratch) + 256;
+static_assert(kHbSmem <= 232448, "k_head_bwd_tc shared memory");
 
 template <bool DYN>
 __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_t cfg, HeadBwdArgs a) {
@@ -89,18 +150,20 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
   float* abuf = smem;
   float* wbuf = abuf + kHbBufs * kOpFloats;
   float* cst = wbuf + kHbSlots * kHbWSlot;
-  float* part = cst + kHbCst;       // [4][3][128] partial output dots
-  float* go = part + 4 * 3 * kTileM;  // [3][128] d loss / d (pre-sigmoid output)
-  TileScratch<kTileM>& scr = *reinterpret_cast<TileScratch<kTileM>*>(go + 3 * kTileM);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(&scr) + sizeof(TileScratch<kTileM>));
-  uint64_t* bar_free = bars;      // [kHbBufs]
-  uint64_t* bar_w = bars + 3;     // [kHbSlots]
-  uint64_t* bar_full = bars + 7;  // [kHbBufs]
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* part0 = cst + kHbCst;            // [2][4][3][128] partial output dots
+  float* go0 = part0 + 2 * 4 * 3 * kTileM;  // [2][3][128] d loss / d (pre-sigmoid output)
+  BwdScratch* scrv = reinterpret_cast<BwdScratch*>(go0 + 2 * 3 * kTileM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scrv + 2);
+  uint64_t* bar_free = bars;       // [kHbBufs]
+  uint64_t* bar_w = bars + 3;      // [kHbSlots]
+  uint64_t* bar_full = bars + 7;   // [kHbBufs]
+  uint64_t* bar_stage = bars + 10; // [2 contexts][4 groups]
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 18);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < 7; ++i) umma::mbar_init(&bars[i], 1);
     for (int i = 0; i < 3; ++i) umma::mbar_init(&bar_full[i], kProdThreads / 32);
+    for (int i = 0; i < 8; ++i) umma::mbar_init(&bar_stage[i], 1);
     umma::fence_mbar_init();
   }
   for (int i = tid; i < kHbCst; i += kTc3Threads) cst[i] = __ldg(a.cst + i);
@@ -112,7 +175,6 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
   const int count = *a.active_count;
   const int ntiles = (count + kTileM - 1) / kTileM;
   const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const uint32_t total_chunks = (uint32_t)my_tiles * HB::kChunks;
   const float* b1 = cst;
   const float* b2 = cst + 128;
   const float* W3t = cst + 256;   // [128][3]
@@ -120,25 +182,62 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
   const float* b3 = cst + 649;
 
   if (warp == kProdThreads / 32) {
-    // ===================== tensor-core warp =====================
-    if (lane == 0 && total_chunks > 0) {
-      for (uint32_t c = 0; c + 1 < kHbSlots && c < total_chunks; ++c) {
-        const int j0 = (int)(c % HB::kChunks);
-        ring_prefetch_w(ring, c, a.wq + HB::woff(j0), 2u * HB::n(j0) * HB::rows(j0) * 4u);
+    // ===================== tensor-core warp: follows the stage sequence chunk by chunk =====================
+    if (lane == 0 && my_tiles > 0) {
+      // chunk cursor = (stage sequence position, index inside the stage); `pf` runs kHbSlots - 1 chunks ahead for the weights
+      struct Cur {
+        HeadStageSeq sq;
+        int i, n, j0;
+        bool ok;
+        __device__ __forceinline__ void load() {   // first chunk / chunk count of the current stage
+          n = sq.stage == 0 ? HB::kNL1 : (sq.stage == 4 ? 0 : 4);
+          j0 = sq.stage == 0 ? 0 : HB::kNL1 + 4 * (sq.stage - 1);
+        }
+        __device__ __forceinline__ void start(int T) {
+          sq.init(T);
+          i = 0;
+          n = 0;
+          ok = true;
+          adv();
+        }
+        __device__ __forceinline__ void adv() {   // move to the next chunk of the sequence
+          ++i;
+          while (ok && i >= n) {
+            ok = sq.next();
+            if (ok) load();
+            i = 0;
+          }
+        }
+        __device__ __forceinline__ int j() const { return j0 + i; }
+      };
+      Cur cu, pf;
+      cu.start(my_tiles);
+      pf.start(my_tiles);
+      for (uint32_t c = 0; c + 1 < kHbSlots && pf.ok; ++c) {
+        const int pj = pf.j();
+        ring_prefetch_w(ring, c, a.wq + HB::woff(pj), 2u * HB::n(pj) * HB::rows(pj) * 4u);
+        pf.adv();
       }
-      for (uint32_t c = 0; c < total_chunks; ++c) {
-        const int j = (int)(c % HB::kChunks);
+      for (uint32_t c = 0; cu.ok; ++c) {
+        const int j = cu.j(), s = cu.sq.ctx;
+        const uint32_t col = (uint32_t)(s * kHbCtxCols);
         ring.chunk = c;
         umma::mbar_wait(&bar_full[c % kHbBufs], (c / kHbBufs) & 1);
-        if (j < kL2) ring_issue<128>(ring, HB::rows(j), 0u, j == 0);
-        else if (j < kD2) ring_issue<128>(ring, 32, 128u, j == kL2);
-        else if (j < kD1) ring_issue<128>(ring, 32, 256u, j == kD2);
-        else if (DYN) ring_issue<32>(ring, 32, 384u, j == kD1);
-        else ring_issue<160>(ring, 32, 0u, j == kD1);  // acc1 / acc2 are dead by now (see epilogue 3)
-        if (c + kHbSlots - 1 < total_chunks) {
-          const int nj = (int)((c + kHbSlots - 1) % HB::kChunks);
-          ring_prefetch_w(ring, c + kHbSlots - 1, a.wq + HB::woff(nj), 2u * HB::n(nj) * HB::rows(nj) * 4u);
+        if (j < kL2) ring_issue<128>(ring, HB::rows(j), col, j == 0);
+        else if (j < kD2) ring_issue<128>(ring, 32, col + 128u, j == kL2);
+        else if (j < kD1) ring_issue<128>(ring, 32, col + 128u, j == kD2);   // acc3 over acc2
+        else if (DYN) ring_issue<32>(ring, 32, col, j == kD1);               // acc4 over acc1
+        else ring_issue<160>(ring, 32, col, j == kD1);
+        if (j == kL2 - 1) umma::commit(&bar_stage[s * 4 + 0]);
+        else if (j == kD2 - 1) umma::commit(&bar_stage[s * 4 + 1]);
+        else if (j == kD1 - 1) umma::commit(&bar_stage[s * 4 + 2]);
+        else if (j == HB::kChunks - 1) umma::commit(&bar_stage[s * 4 + 3]);
+        if (pf.ok) {
+          const int pj = pf.j();
+          ring_prefetch_w(ring, c + kHbSlots - 1, a.wq + HB::woff(pj), 2u * HB::n(pj) * HB::rows(pj) * 4u);
+          pf.adv();
         }
+        cu.adv();
       }
     }
     __syncwarp();
@@ -155,121 +254,129 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
 #pragma unroll
     for (int i = 0; i < 3; ++i) acc_b3[i] = 0.f;
 
-    auto wait_chunk = [&](uint32_t c) {
-      umma::mbar_wait_backoff(&bar_free[c % kHbBufs], (c / kHbBufs) & 1);
-      umma::fence_after_sync();
-    };
     auto arrive = [&]() {
+      umma::fence_before_sync();   // orders this warp's tcgen05.ld before the MMAs that follow the arrival
       umma::fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[ring.chunk % kHbBufs]);
       ring.chunk++;
     };
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int jg0 = tile * kTileM;
-      if (tid < kTileM) {
-        const int jg = jg0 + tid;
-        const bool in = jg < count;
-        const int i = in ? __ldg(a.active_idx + jg) : 0;
-        scr.idx[tid] = i;
-        scr.ray[tid] = in ? i / a.S : -1;
-        scr.on[tid] = in ? 1 : 0;
-        float vd[3] = {0.f, 0.f, 0.f};
-        if (in) ray_viewdir(a.rays, i / a.S, vd);
-#pragma unroll
-        for (int ax = 0; ax < 3; ++ax) {
-          const float x = in ? __ldg(a.xyz + (size_t)i * 3 + ax) : 0.f;
-          scr.xn[ax][tid] = in ? norm_coord(x, nb.mn[ax], nb.inv[ax]) : 0.f;
-          scr.xu[ax][tid] = vd[ax];
-        }
-      }
-      prod_bar();
-      const uint32_t base = ring.chunk;
-      float f[8];  // static head: this thread's 8 basis outputs (features 8 cb .. 8 cb + 7), kept for epilogue 4
-      if (DYN) {
-        // ---- L1 operand: 3 position/time chunks (also streamed to X1T rows 0..79) + the feat chunk (X1T rows 80..111 <- featT)
+    HeadStageSeq sq;
+    sq.init(my_tiles);
 #pragma unroll 1
-        for (int j = 0; j < 3; ++j) {
-          ring_wait_free(ring);
-          float* buf = ring_abuf(ring);
-          const int u0 = j * 5, nu = (j == 2) ? 4 : 5;
-          for (int u = prt; u < nu; u += 4) produce_pos_unit(u0 + u, scr, a.tfeat, m, buf, a.X1T + (size_t)(j * 32) * ld, ld, jg0 + m);
-          arrive();
-        }
-        {
-          ring_wait_free(ring);
-          float* buf = ring_abuf(ring);
-          const bool on = scr.on[m] != 0;
-          for (int qq = prt; qq < 8; qq += 4) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (on) {
-              const float* fp = a.featT + (size_t)(qq * 4) * ld + jg0 + m;
-              v = make_float4(__ldg(fp), __ldg(fp + ld), __ldg(fp + 2 * (size_t)ld), __ldg(fp + 3 * (size_t)ld));
-            }
-            store_quad(buf, m, qq, v);
-            store_quad_g(a.X1T, ld, 80 + qq * 4, jg0 + m, v);
+    while (sq.next()) {
+      const int s = sq.ctx;
+      BwdScratch& scr = scrv[s];
+      float* part = part0 + s * (4 * 3 * kTileM);
+      float* go = go0 + s * (3 * kTileM);
+      const uint32_t tcol = ring.tmem + (uint32_t)(s * kHbCtxCols) + ((uint32_t)(q * 32) << 16);
+      const uint32_t par = (uint32_t)((sq.tile >> 1) & 1);
+      const int jg0 = ((int)blockIdx.x + sq.tile * (int)gridDim.x) * kTileM;
+      if (sq.stage == 0) {
+        prod_bar();   // every warp is done with this context's scratch (E4 of its previous tile)
+        if (tid < kTileM) {
+          const int jg = jg0 + tid;
+          const bool in = jg < count;
+          const int i = in ? __ldg(a.active_idx + jg) : 0;
+          scr.idx[tid] = i;
+          scr.ray[tid] = in ? i / a.S : -1;
+          scr.on[tid] = in ? 1 : 0;
+          float vd[3] = {0.f, 0.f, 0.f};
+          if (in) ray_viewdir(a.rays, i / a.S, vd);
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) {
+            const float x = in ? __ldg(a.xyz + (size_t)i * 3 + ax) : 0.f;
+            scr.xn[ax][tid] = in ? norm_coord(x, nb.mn[ax], nb.inv[ax]) : 0.f;
+            scr.xu[ax][tid] = vd[ax];
           }
-          if (prt == 0) a.X1T[(size_t)112 * ld + jg0 + m] = on ? 1.f : 0.f;  // ones row: its weight-gradient column is d b1
-          arrive();
         }
-      } else {
-        // ---- L1 operand: 4 encoding chunks (chunk c <- warps with cb == c) + the [features | viewdir] chunk; X1T rows 0..159
-        const bool on = scr.on[em] != 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = on ? __ldg(a.featT + (size_t)(cb * 8 + i) * ld + jg0 + em) : 0.f;
+        prod_bar();
+        if (DYN) {
+          // ---- L1 operand: 3 position/time chunks (also streamed to X1T rows 0..79) + the feat chunk (X1T rows 80..111 <- featT)
 #pragma unroll 1
-        for (int c4 = 0; c4 < 4; ++c4) {
-          ring_wait_free(ring);
-          if (c4 == cb) {
+          for (int j = 0; j < 3; ++j) {
+            ring_wait_free(ring);
             float* buf = ring_abuf(ring);
+            const int u0 = j * 5, nu = (j == 2) ? 4 : 5;
+            for (int u = prt; u < nu; u += 4) produce_pos_unit(u0 + u, scr, a.tfeat, m, buf, a.X1T + (size_t)(j * 32) * ld, ld, jg0 + m);
+            arrive();
+          }
+          {
+            ring_wait_free(ring);
+            float* buf = ring_abuf(ring);
+            const bool on = scr.on[m] != 0;
+            for (int qq = prt; qq < 8; qq += 4) {
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (on) {
+                const float* fp = a.featT + (size_t)(qq * 4) * ld + jg0 + m;
+                v = make_float4(__ldg(fp), __ldg(fp + ld), __ldg(fp + 2 * (size_t)ld), __ldg(fp + 3 * (size_t)ld));
+              }
+              store_quad(buf, m, qq, v);
+              store_quad_g(a.X1T, ld, 80 + qq * 4, jg0 + m, v);
+            }
+            if (prt == 0) a.X1T[(size_t)112 * ld + jg0 + m] = on ? 1.f : 0.f;  // ones row: its weight-gradient column is d b1
+            arrive();
+          }
+        } else {
+          // ---- L1 operand: 4 encoding chunks (chunk c <- warps with cb == c) + the [features | viewdir] chunk; X1T rows 0..159
+          const bool on = scr.on[em] != 0;
+          float f[8];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {   // frequency 1, 2
-              float sv[8], cv[8];
+          for (int i = 0; i < 8; ++i) f[i] = on ? __ldg(a.featT + (size_t)(cb * 8 + i) * ld + jg0 + em) : 0.f;
+#pragma unroll 1
+          for (int c4 = 0; c4 < 4; ++c4) {
+            ring_wait_free(ring);
+            if (c4 == cb) {
+              float* buf = ring_abuf(ring);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) sincosf(h ? f[i] * 2.0f : f[i], &sv[i], &cv[i]);
+              for (int h = 0; h < 2; ++h) {   // frequency 1, 2
+                float sv[8], cv[8];
 #pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                const float4 s4 = make_float4(sv[half * 4], sv[half * 4 + 1], sv[half * 4 + 2], sv[half * 4 + 3]);
-                const float4 c4v = make_float4(cv[half * 4], cv[half * 4 + 1], cv[half * 4 + 2], cv[half * 4 + 3]);
-                store_quad(buf, em, h * 2 + half, s4);
-                store_quad(buf, em, 4 + h * 2 + half, c4v);
-                store_quad_g(a.X1T, ld, cb * 32 + (h * 2 + half) * 4, jg0 + em, s4);
-                store_quad_g(a.X1T, ld, cb * 32 + (4 + h * 2 + half) * 4, jg0 + em, c4v);
+                for (int i = 0; i < 8; ++i) sincosf(h ? f[i] * 2.0f : f[i], &sv[i], &cv[i]);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                  const float4 s4 = make_float4(sv[half * 4], sv[half * 4 + 1], sv[half * 4 + 2], sv[half * 4 + 3]);
+                  const float4 c4v = make_float4(cv[half * 4], cv[half * 4 + 1], cv[half * 4 + 2], cv[half * 4 + 3]);
+                  store_quad(buf, em, h * 2 + half, s4);
+                  store_quad(buf, em, 4 + h * 2 + half, c4v);
+                  store_quad_g(a.X1T, ld, cb * 32 + (h * 2 + half) * 4, jg0 + em, s4);
+                  store_quad_g(a.X1T, ld, cb * 32 + (4 + h * 2 + half) * 4, jg0 + em, c4v);
+                }
               }
             }
+            arrive();
+          }
+          ring_wait_free(ring);
+          {
+            float* buf = ring_abuf(ring);
+            float4 v0 = make_float4(f[0], f[1], f[2], f[3]), v1 = make_float4(f[4], f[5], f[6], f[7]);
+            if (cb == 3) {  // rows 27..29: view direction (zero weights for the time-embedding head)
+              v0.w = on ? scr.xu[0][em] : 0.f;
+              v1.x = on ? scr.xu[1][em] : 0.f;
+              v1.y = on ? scr.xu[2][em] : 0.f;
+            }
+            store_quad(buf, em, cb * 2, v0);
+            store_quad(buf, em, cb * 2 + 1, v1);
+            store_quad_g(a.X1T, ld, 128 + cb * 8, jg0 + em, v0);
+            store_quad_g(a.X1T, ld, 128 + cb * 8 + 4, jg0 + em, v1);
+            if (cb == 0) a.X1T[(size_t)160 * ld + jg0 + em] = on ? 1.f : 0.f;
           }
           arrive();
         }
-        ring_wait_free(ring);
-        {
-          float* buf = ring_abuf(ring);
-          float4 v0 = make_float4(f[0], f[1], f[2], f[3]), v1 = make_float4(f[4], f[5], f[6], f[7]);
-          if (cb == 3) {  // rows 27..29: view direction (zero weights for the time-embedding head)
-            v0.w = on ? scr.xu[0][em] : 0.f;
-            v1.x = on ? scr.xu[1][em] : 0.f;
-            v1.y = on ? scr.xu[2][em] : 0.f;
-          }
-          store_quad(buf, em, cb * 2, v0);
-          store_quad(buf, em, cb * 2 + 1, v1);
-          store_quad_g(a.X1T, ld, 128 + cb * 8, jg0 + em, v0);
-          store_quad_g(a.X1T, ld, 128 + cb * 8 + 4, jg0 + em, v1);
-          if (cb == 0) a.X1T[(size_t)160 * ld + jg0 + em] = on ? 1.f : 0.f;
-        }
-        arrive();
-      }
-      // ---- epilogue 1: h1 = relu(acc1 + b1) -> L2 operand chunk cb, H1T
-      wait_chunk(base + kL2 - 1);
-      {
+      } else if (sq.stage == 1) {
+        // ---- epilogue 1: h1 = relu(acc1 + b1) -> L2 operand chunk cb, H1T
+        umma::mbar_wait_backoff(&bar_stage[s * 4 + 0], par);
+        umma::fence_after_sync();
         float r[32];
-        umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 32, r);
+        umma::tmem_ld32(tcol + cb * 32, r);
         const bool on = scr.on[em] != 0;
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) r[jj] = on ? fmaxf(r[jj] + b1[cb * 32 + jj], 0.f) : 0.f;
 #pragma unroll 1
         for (int c4 = 0; c4 < 4; ++c4) {
           // every warp waits for the slot's previous use before arriving: an early arrival meant for chunk c would
-          // otherwise be counted in the still-open phase of chunk c-3 on the same barrier
+          // otherwise be counted in the still-open phase of an older chunk on the same barrier
           ring_wait_free(ring);
           if (c4 == cb) {
             float* buf = ring_abuf(ring);
@@ -282,12 +389,12 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
           }
           arrive();
         }
-      }
-      // ---- epilogue 2: h2 = relu(acc2 + b2); output layer; d(out); dH2 -> dgrad-2 operand chunk cb
-      wait_chunk(base + kD2 - 1);
-      {
+      } else if (sq.stage == 2) {
+        // ---- epilogue 2: h2 = relu(acc2 + b2); output layer; d(out); dH2 -> dgrad-2 operand chunk cb
+        umma::mbar_wait_backoff(&bar_stage[s * 4 + 1], par);
+        umma::fence_after_sync();
         float h2[32];
-        umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + 128 + cb * 32, h2);
+        umma::tmem_ld32(tcol + 128 + cb * 32, h2);
         const bool on = scr.on[em] != 0;
         float po[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -355,18 +462,18 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
           }
           arrive();
         }
-      }
-      // ---- epilogue 3: dH1 = acc3 * [h1 > 0] -> dgrad-1 operand chunk cb, DH1T.  All TMEM reads (acc3 and the sign of
-      // acc1) finish before any warp arrives on the first dgrad-1 chunk: the static head's dgrad-1 GEMM overwrites acc1 / acc2.
-      wait_chunk(base + kD1 - 1);
-      {
+      } else if (sq.stage == 3) {
+        // ---- epilogue 3: dH1 = acc3 * [h1 > 0] -> dgrad-1 operand chunk cb, DH1T.  All TMEM reads (acc3 and the sign of
+        // acc1) finish before any warp arrives on the first dgrad-1 chunk: the dgrad-1 GEMM overwrites acc1 (and acc3's first columns).
+        umma::mbar_wait_backoff(&bar_stage[s * 4 + 2], par);
+        umma::fence_after_sync();
         float r3[32];
         const bool on = scr.on[em] != 0;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           float t3[16], t1[16];
-          umma::tmem_ld16(ring.tmem + ((uint32_t)(q * 32) << 16) + 256 + cb * 32 + hf * 16, t3);
-          umma::tmem_ld16(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 32 + hf * 16, t1);
+          umma::tmem_ld16(tcol + 128 + cb * 32 + hf * 16, t3);
+          umma::tmem_ld16(tcol + cb * 32 + hf * 16, t1);
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) r3[hf * 16 + jj] = (on && (t1[jj] + b1[cb * 32 + hf * 16 + jj]) > 0.f) ? t3[jj] : 0.f;
         }
@@ -386,51 +493,53 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
           }
           arrive();
         }
-      }
-      // ---- epilogue 4: dfeat
-      wait_chunk(base + HB::kChunks - 1);
-      if (DYN) {
-        if (cb == 0) {
-          float r4[32];
-          umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + 384, r4);
-#pragma unroll
-          for (int qq = 0; qq < 8; ++qq) {
-            float4 v = make_float4(r4[qq * 4], r4[qq * 4 + 1], r4[qq * 4 + 2], r4[qq * 4 + 3]);
-            if (qq == 6) v.w = 0.f;            // only 27 feature rows carry a gradient
-            if (qq == 7) v = make_float4(0.f, 0.f, 0.f, 0.f);
-            store_quad_g(a.DFT, ld, qq * 4, jg0 + em, v);
-          }
-        }
       } else {
-        // dX columns: [32 cb, 32 cb + 32) = d(sin f, sin 2f, cos f, cos 2f) of this thread's 8 features, [128 + 8 cb, +8) = d f
-        float dx[32], df[8];
-        umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 32, dx);
-        tmem_ld8_(ring.tmem + ((uint32_t)(q * 32) << 16) + 128 + cb * 8, df);
-        const bool on = scr.on[em] != 0;
-        if (cb == 3 && on && a.gvd) {
-          const int ry = scr.ray[em];
-          atomicAdd(a.gvd + (size_t)ry * 3 + 0, df[3]);
-          atomicAdd(a.gvd + (size_t)ry * 3 + 1, df[4]);
-          atomicAdd(a.gvd + (size_t)ry * 3 + 2, df[5]);
-        }
+        // ---- epilogue 4: dfeat
+        umma::mbar_wait_backoff(&bar_stage[s * 4 + 3], par);
+        umma::fence_after_sync();
+        if (DYN) {
+          if (cb == 0) {
+            float r4[32];
+            umma::tmem_ld32(tcol, r4);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float s1, c1, s2, c2;
-          sincosf(f[i], &s1, &c1);
-          sincosf(f[i] * 2.0f, &s2, &c2);
-          // d/df [sin f, sin 2f, cos f, cos 2f] = [cos f, 2 cos 2f, -sin f, -2 sin 2f]
-          float g = df[i];
-          g = fmaf(dx[i], c1, g);
-          g = fmaf(dx[8 + i], 2.0f * c2, g);
-          g = fmaf(dx[16 + i], -s1, g);
-          g = fmaf(dx[24 + i], -2.0f * s2, g);
-          df[i] = (on && cb * 8 + i < 27) ? g : 0.f;
+            for (int qq = 0; qq < 8; ++qq) {
+              float4 v = make_float4(r4[qq * 4], r4[qq * 4 + 1], r4[qq * 4 + 2], r4[qq * 4 + 3]);
+              if (qq == 6) v.w = 0.f;            // only 27 feature rows carry a gradient
+              if (qq == 7) v = make_float4(0.f, 0.f, 0.f, 0.f);
+              store_quad_g(a.DFT, ld, qq * 4, jg0 + em, v);
+            }
+          }
+        } else {
+          // dX columns: [32 cb, 32 cb + 32) = d(sin f, sin 2f, cos f, cos 2f) of this thread's 8 features, [128 + 8 cb, +8) = d f
+          float dx[32], df[8];
+          umma::tmem_ld32(tcol + cb * 32, dx);
+          tmem_ld8_(tcol + 128 + cb * 8, df);
+          const bool on = scr.on[em] != 0;
+          if (cb == 3 && on && a.gvd) {
+            const int ry = scr.ray[em];
+            atomicAdd(a.gvd + (size_t)ry * 3 + 0, df[3]);
+            atomicAdd(a.gvd + (size_t)ry * 3 + 1, df[4]);
+            atomicAdd(a.gvd + (size_t)ry * 3 + 2, df[5]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float fi = on ? __ldg(a.featT + (size_t)(cb * 8 + i) * ld + jg0 + em) : 0.f;   // the basis output again (L2 hit)
+            float s1, c1, s2, c2;
+            sincosf(fi, &s1, &c1);
+            sincosf(fi * 2.0f, &s2, &c2);
+            // d/df [sin f, sin 2f, cos f, cos 2f] = [cos f, 2 cos 2f, -sin f, -2 sin 2f]
+            float g = df[i];
+            g = fmaf(dx[i], c1, g);
+            g = fmaf(dx[8 + i], 2.0f * c2, g);
+            g = fmaf(dx[16 + i], -s1, g);
+            g = fmaf(dx[24 + i], -2.0f * s2, g);
+            df[i] = (on && cb * 8 + i < 27) ? g : 0.f;
+          }
+          store_quad_g(a.DFT, ld, cb * 8, jg0 + em, make_float4(df[0], df[1], df[2], df[3]));
+          store_quad_g(a.DFT, ld, cb * 8 + 4, jg0 + em, make_float4(df[4], df[5], df[6], df[7]));
         }
-        store_quad_g(a.DFT, ld, cb * 8, jg0 + em, make_float4(df[0], df[1], df[2], df[3]));
-        store_quad_g(a.DFT, ld, cb * 8 + 4, jg0 + em, make_float4(df[4], df[5], df[6], df[7]));
+        umma::fence_before_sync();
       }
-      umma::fence_before_sync();
-      prod_bar();
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) atomicAdd(a.gw3h + c * 128 + cb * 32 + lane, acc_w3[c]);

@@ -449,16 +449,17 @@ k_dyn_sigma_blend_tc2(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, co
             store_quad(buf, m, prt, r);
             if (XT) store_quad_g(XT, ld, xrow + prt * 4, tile * kTileM + m, r);
           }
-          if (prt < 2) {
-            const float* pp = prt == 0 ? (isbl ? vbl.plane[1] : vden.plane[1]) : (isbl ? vbl.plane[2] : vden.plane[2]);
-            const float* ll = prt == 0 ? (isbl ? vbl.line[1] : vden.line[1]) : (isbl ? vbl.line[2] : vden.line[2]);
+          if ((prt >> 1) == (isbl ? 1 : 0)) {   // the two 4-channel planes: threads 0,1 in density chunks, threads 2,3 in blending chunks
+            const int pw = prt & 1;
+            const float* pp = pw == 0 ? (isbl ? vbl.plane[1] : vden.plane[1]) : (isbl ? vbl.plane[2] : vden.plane[2]);
+            const float* ll = pw == 0 ? (isbl ? vbl.line[1] : vden.line[1]) : (isbl ? vbl.line[2] : vden.line[2]);
             float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
             // plane 1: (u,v,l) = (x,z,y), W = Gx; plane 2: (y,z,x), W = Gy
             if (act)
-              r = vm_group_f(pp, ll, 4, plane_st(vden, prt == 0 ? 1 : 2), load_tap(taps, si, prt == 0 ? 0 : 1, m), load_tap(taps, si, 2, m),
-                             load_tap(taps, si, prt == 0 ? 1 : 0, m), 0);
-            store_quad(buf, m, 4 + prt, r);
-            if (XT) store_quad_g(XT, ld, xrow + 16 + prt * 4, tile * kTileM + m, r);
+              r = vm_group_f(pp, ll, 4, plane_st(vden, pw == 0 ? 1 : 2), load_tap(taps, si, pw == 0 ? 0 : 1, m), load_tap(taps, si, 2, m),
+                             load_tap(taps, si, pw == 0 ? 1 : 0, m), 0);
+            store_quad(buf, m, 4 + pw, r);
+            if (XT) store_quad_g(XT, ld, xrow + 16 + pw * 4, tile * kTileM + m, r);
           }
         }
         umma::fence_async_smem();
