@@ -194,6 +194,15 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
       ring.chunk++;
     };
 
+    // the active-list entry of the NEXT tile is fetched one iteration ahead (threads 0..127): it heads the dependent-load chain
+    // of S0 (index -> position / direction), during which the other twelve warps wait at the stage's barrier
+    int i_pref = 0;
+    bool in_pref = false;
+    if (tid < kTileM && my_tiles > 0) {
+      const int jg = (int)blockIdx.x * kTileM + tid;
+      in_pref = jg < count;
+      i_pref = in_pref ? __ldg(a.active_idx + jg) : 0;
+    }
 #pragma unroll 1
     for (int k = 0; k <= my_tiles; ++k) {
       const bool hasY = k < my_tiles, hasX = k >= 1;
@@ -207,9 +216,13 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
       if (hasY) {
         // ---- S0(Y): per-sample scratch, taps
         if (tid < kTileM) {
-          const int jg = jgY + tid;
-          const bool in = jg < count;
-          const int i = in ? __ldg(a.active_idx + jg) : 0;
+          const bool in = in_pref;
+          const int i = i_pref;
+          if (k + 1 < my_tiles) {
+            const int jgn = jgY + (int)gridDim.x * kTileM + tid;
+            in_pref = jgn < count;
+            i_pref = in_pref ? __ldg(a.active_idx + jgn) : 0;
+          }
           scrY.idx[tid] = i;
           scrY.ray[tid] = in ? i / a.S : -1;
           scrY.on[tid] = in ? 1 : 0;
@@ -313,17 +326,19 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
           store_quad_g(a.featT, ld, cb * 8 + 4, jgY + em, make_float4(f[4], f[5], f[6], f[7]));
         }
         if (!DYN) {
+          // the encodings are computed BEFORE the ring wait: chunk c4 is written by the warps with cb == c4 only, and with three
+          // operand buffers the cb == 3 warps otherwise start their 16 sincosf after chunk 0's MMAs (14.8 % of the stall samples)
+          float s1[8], c1[8], s2[8], c2[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            sincosf(f[i], &s1[i], &c1[i]);
+            sincosf(f[i] * 2.0f, &s2[i], &c2[i]);
+          }
 #pragma unroll 1
           for (int c4 = 0; c4 < 4; ++c4) {
             ring_wait_free(ring);
             if (c4 == cb) {
               float* buf = ring_abuf(ring);
-              float s1[8], c1[8], s2[8], c2[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                sincosf(f[i], &s1[i], &c1[i]);
-                sincosf(f[i] * 2.0f, &s2[i], &c2[i]);
-              }
               store_quad(buf, em, 0, make_float4(s1[0], s1[1], s1[2], s1[3]));
               store_quad(buf, em, 1, make_float4(s1[4], s1[5], s1[6], s1[7]));
               store_quad(buf, em, 2, make_float4(s2[0], s2[1], s2[2], s2[3]));

@@ -324,24 +324,32 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
           float f[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = on ? __ldg(a.featT + (size_t)(cb * 8 + i) * ld + jg0 + em) : 0.f;
+          // encodings first (and their X1T stream), ring wait afterwards: the warps with cb == 3 would otherwise start their
+          // sincosf only when chunk 0's MMAs have released an operand buffer
+          float sv[2][8], cv[2][8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {   // frequency 1, 2
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sincosf(h ? f[i] * 2.0f : f[i], &sv[h][i], &cv[h][i]);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              store_quad_g(a.X1T, ld, cb * 32 + (h * 2 + half) * 4, jg0 + em,
+                           make_float4(sv[h][half * 4], sv[h][half * 4 + 1], sv[h][half * 4 + 2], sv[h][half * 4 + 3]));
+              store_quad_g(a.X1T, ld, cb * 32 + (4 + h * 2 + half) * 4, jg0 + em,
+                           make_float4(cv[h][half * 4], cv[h][half * 4 + 1], cv[h][half * 4 + 2], cv[h][half * 4 + 3]));
+            }
+          }
 #pragma unroll 1
           for (int c4 = 0; c4 < 4; ++c4) {
             ring_wait_free(ring);
             if (c4 == cb) {
               float* buf = ring_abuf(ring);
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {   // frequency 1, 2
-                float sv[8], cv[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) sincosf(h ? f[i] * 2.0f : f[i], &sv[i], &cv[i]);
+              for (int h = 0; h < 2; ++h) {
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                  const float4 s4 = make_float4(sv[half * 4], sv[half * 4 + 1], sv[half * 4 + 2], sv[half * 4 + 3]);
-                  const float4 c4v = make_float4(cv[half * 4], cv[half * 4 + 1], cv[half * 4 + 2], cv[half * 4 + 3]);
-                  store_quad(buf, em, h * 2 + half, s4);
-                  store_quad(buf, em, 4 + h * 2 + half, c4v);
-                  store_quad_g(a.X1T, ld, cb * 32 + (h * 2 + half) * 4, jg0 + em, s4);
-                  store_quad_g(a.X1T, ld, cb * 32 + (4 + h * 2 + half) * 4, jg0 + em, c4v);
+                  store_quad(buf, em, h * 2 + half, make_float4(sv[h][half * 4], sv[h][half * 4 + 1], sv[h][half * 4 + 2], sv[h][half * 4 + 3]));
+                  store_quad(buf, em, 4 + h * 2 + half, make_float4(cv[h][half * 4], cv[h][half * 4 + 1], cv[h][half * 4 + 2], cv[h][half * 4 + 3]));
                 }
               }
             }

@@ -343,8 +343,17 @@ constexpr int kSbWFloats = sb_woff(kSbChunks);
 // barrier in the steady state; producers use a named barrier (id 1) among themselves for the per-tile scratch.
 // The bilinear taps depend only on (axis, stride) -- 9 per sample -- and are computed once per tile into shared memory.
 
-constexpr size_t kSb2Smem = (size_t)(3 * kOpFloats + 2 * kWSlotFloats + 4 * kTileM + 256) * sizeof(float) + sizeof(TapsSmem) +
-                            sizeof(TileScratch<kTileM>) + 128;
+// Two tiles in flight (see tc_app_fwd.cu): iteration k produces the nine operand chunks of tile Y = k (context k & 1: its own
+// scratch, taps and 128 TMEM columns) and then reads back / finishes tile X = k - 1, whose last MMAs have long retired by then
+// (the read-back wait was 9.6 % of the stall samples of the one-tile kernel).  The chunk order in the ring is unchanged.
+struct SbScratch {
+  float xn[3][kTileM];  // normalize(xyz)
+  float xq[3][kTileM];  // normalize(xyz_prime)
+  int ray[kTileM], on[kTileM];
+};
+constexpr size_t kSb2Smem = (size_t)(3 * kOpFloats + 2 * kWSlotFloats + 2 * 4 * kTileM + 256) * sizeof(float) + 2 * sizeof(TapsSmem) +
+                            2 * sizeof(SbScratch) + 128;
+static_assert(kSb2Smem <= 232448, "k_dyn_sigma_blend_tc2 shared memory");
 
 __global__ void __launch_bounds__(kTc3Threads, 1)
 k_dyn_sigma_blend_tc2(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, const float* __restrict__ wq /*kSbWFloats*/,
@@ -356,30 +365,32 @@ k_dyn_sigma_blend_tc2(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, co
   extern __shared__ __align__(128) float smem[];
   float* abuf = smem;
   float* wbuf = abuf + 3 * kOpFloats;
-  float* part = wbuf + 2 * kWSlotFloats;  // [4][128] partial dots
-  float* cst = part + 4 * kTileM;         // b1cat[128] | w2cat[128]
-  TapsSmem& taps = *reinterpret_cast<TapsSmem*>(cst + 256);
-  TileScratch<kTileM>& scr = *reinterpret_cast<TileScratch<kTileM>*>(reinterpret_cast<uint8_t*>(&taps) + sizeof(TapsSmem));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(&scr) + sizeof(TileScratch<kTileM>));
-  uint64_t* bar_free = bars;      // [3]
-  uint64_t* bar_w = bars + 3;     // [2]
-  uint64_t* bar_full = bars + 5;  // [3]
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* part0 = wbuf + 2 * kWSlotFloats;  // [2][4][128] partial dots
+  float* cst = part0 + 2 * 4 * kTileM;     // b1cat[128] | w2cat[128]
+  TapsSmem* tapsv = reinterpret_cast<TapsSmem*>(cst + 256);
+  SbScratch* scrv = reinterpret_cast<SbScratch*>(tapsv + 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scrv + 2);
+  uint64_t* bar_free = bars;       // [3]
+  uint64_t* bar_w = bars + 3;      // [2]
+  uint64_t* bar_full = bars + 5;   // [3]
+  uint64_t* bar_stage = bars + 8;  // [2]: the tile of context s is complete in TMEM
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 10);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) umma::mbar_init(&bars[i], 1);
     for (int i = 0; i < 3; ++i) umma::mbar_init(&bar_full[i], kProdThreads / 32);
+    for (int i = 0; i < 2; ++i) umma::mbar_init(&bar_stage[i], 1);
     umma::fence_mbar_init();
   }
   if (tid < 128) cst[tid] = __ldg(b1cat + tid);
   else if (tid < 256) cst[tid] = __ldg(w2cat + tid - 128);
-  if (warp == 0) umma::tmem_alloc(tslot, 128);
+  if (warp == 0) umma::tmem_alloc(tslot, 256);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   Ring ring{bar_free, bar_w, abuf, wbuf, 0u, *tslot};
   const int ntiles = (P + kTileM - 1) / kTileM;
-  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const uint32_t total_chunks = (uint32_t)my_tiles * kSbChunks;
 
   if (warp == kProdThreads / 32) {
@@ -388,11 +399,13 @@ k_dyn_sigma_blend_tc2(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, co
       ring_prefetch_w(ring, 0, wq + sb_woff(0), 2u * sb_n(0) * sb_rows(0) * 4u);
       for (uint32_t c = 0; c < total_chunks; ++c) {
         const int j = (int)(c % kSbChunks);
+        const uint32_t ctx = (c / kSbChunks) & 1u, colb = ctx * 128u;
         ring.chunk = c;
         umma::mbar_wait(&bar_full[c % 3], (c / 3) & 1);
         const uint32_t col0 = (j >= 3 && ((j - 3) & 1)) ? 64u : 0u;
-        if (j < 3) ring_issue<128>(ring, sb_rows(j), 0u, j == 0);
-        else ring_issue<64>(ring, sb_rows(j), col0, false);
+        if (j < 3) ring_issue<128>(ring, sb_rows(j), colb, j == 0);
+        else ring_issue<64>(ring, sb_rows(j), colb + col0, false);
+        if (j == kSbChunks - 1) umma::commit(&bar_stage[ctx]);
         if (c + 1 < total_chunks) {
           const int nj = (j + 1) % kSbChunks;
           ring_prefetch_w(ring, c + 1, wq + sb_woff(nj), 2u * sb_n(nj) * sb_rows(nj) * 4u);
@@ -405,112 +418,133 @@ k_dyn_sigma_blend_tc2(dynrf_field_cfg_t cfg, dynrf_vm_t vden, dynrf_vm_t vbl, co
     const int m = tid & (kTileM - 1), prt = tid >> 7;
     const AabbNorm nb = make_norm(cfg);
     const int G[3] = {vden.W[0], vden.H[0], vden.L[0]};
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      if (tid < kTileM) {
-        const int i = tile * kTileM + tid;
-        const bool in = i < P;
-        scr.ray[tid] = in ? i / S : -1;
-        scr.on[tid] = (in && valid[i] != 0) ? 1 : 0;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          const float x = in ? __ldg(xyz + (size_t)i * 3 + a) : 0.f;
-          const float xp = in ? __ldg(xyz_prime + (size_t)i * 3 + a) : 0.f;
-          scr.xn[a][tid] = norm_coord(x, nb.mn[a], nb.inv[a]);
-          scr.xq[a][tid] = norm_coord(xp, nb.mn[a], nb.inv[a]);
-        }
-      }
-      prod_bar();
-      // 9 taps per sample: (stride, axis)
-      for (int item = tid; item < 9 * kTileM; item += kProdThreads) {
-        const int mm = item & (kTileM - 1), t = item >> 7;
-        const int si = t / 3, ax = t % 3;
-        const Tap1 tp = make_tap(scr.xq[ax][mm], ax == 0 ? G[0] : (ax == 1 ? G[1] : G[2]), 1 << si);
-        taps.t[t][mm] = make_int4(tp.i0, tp.i1, __float_as_int(tp.w0), __float_as_int(tp.w1));
-      }
-      prod_bar();
-      const bool act = scr.on[m] != 0;
+    auto arrive = [&]() {
+      umma::fence_before_sync();
+      umma::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[ring.chunk % 3]);
+      ring.chunk++;
+    };
 #pragma unroll 1
-      for (int j = 0; j < kSbChunks; ++j) {
-        ring_wait_free(ring);
-        float* buf = ring_abuf(ring);
-        if (j < 3) {
+    for (int k = 0; k <= my_tiles; ++k) {
+      const bool hasY = k < my_tiles, hasX = k >= 1;
+      const int sy = k & 1, sx = (k - 1) & 1;
+      const int tileY = (int)blockIdx.x + k * (int)gridDim.x, tileX = tileY - (int)gridDim.x;
+      if (hasY) {
+        SbScratch& scr = scrv[sy];
+        TapsSmem& taps = tapsv[sy];
+        if (tid < kTileM) {
+          const int i = tileY * kTileM + tid;
+          const bool in = i < P;
+          scr.ray[tid] = in ? i / S : -1;
+          scr.on[tid] = (in && valid[i] != 0) ? 1 : 0;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const float x = in ? __ldg(xyz + (size_t)i * 3 + a) : 0.f;
+            const float xp = in ? __ldg(xyz_prime + (size_t)i * 3 + a) : 0.f;
+            scr.xn[a][tid] = norm_coord(x, nb.mn[a], nb.inv[a]);
+            scr.xq[a][tid] = norm_coord(xp, nb.mn[a], nb.inv[a]);
+          }
+        }
+        prod_bar();
+        // 9 taps per sample: (stride, axis)
+        for (int item = tid; item < 9 * kTileM; item += kProdThreads) {
+          const int mm = item & (kTileM - 1), t = item >> 7;
+          const int si = t / 3, ax = t % 3;
+          const Tap1 tp = make_tap(scr.xq[ax][mm], ax == 0 ? G[0] : (ax == 1 ? G[1] : G[2]), 1 << si);
+          taps.t[t][mm] = make_int4(tp.i0, tp.i1, __float_as_int(tp.w0), __float_as_int(tp.w1));
+        }
+        prod_bar();
+        const bool act = scr.on[m] != 0;
+        const int tile = tileY;
+#pragma unroll 1
+        for (int j = 0; j < 3; ++j) {
+          ring_wait_free(ring);
+          float* buf = ring_abuf(ring);
           const int u0 = j * 5, nu = (j == 2) ? 4 : 5;
           for (int u = prt; u < nu; u += 4)
             produce_pos_unit(u0 + u, scr, tfeat, m, buf, XT ? XT + (size_t)(j * 32) * ld : nullptr, ld, tile * kTileM + m);
-        } else {
-          const int si = (j - 3) >> 1;
-          const bool isbl = ((j - 3) & 1) != 0;
-          const int xrow = (isbl ? 152 : 80) + si * 24;   // XT rows: 80 position/time | 72 density | 72 blending
-          {
-            const float* pp = isbl ? vbl.plane[0] : vden.plane[0];
-            const float* ll = isbl ? vbl.line[0] : vden.line[0];
-            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (act) r = vm_group_f(pp, ll, 16, plane_st(vden, 0), load_tap(taps, si, 0, m), load_tap(taps, si, 1, m), load_tap(taps, si, 2, m), prt * 4);
+          arrive();
+        }
+        // feature chunks, one (density, blending) pair per stride: both tables are read at the same taps, so the lookups of the
+        // pair are issued together (twice the loads in flight per thread: the first use of a gathered value was 27 % of the stall
+        // samples) and the ring waits come after them.  The two 4-channel planes of a table go to threads 0,1 (density) / 2,3
+        // (blending).
+#pragma unroll 1
+        for (int si = 0; si < 3; ++si) {
+          const TapF tx = load_tap(taps, si, 0, m), ty = load_tap(taps, si, 1, m), tz = load_tap(taps, si, 2, m);
+          float4 rd = make_float4(0.f, 0.f, 0.f, 0.f), rb = rd, rs = rd;
+          const int pw = prt & 1;
+          const bool sbl = (prt >> 1) != 0;   // this thread's small plane belongs to the blending table
+          if (act) {
+            rd = vm_group_f(vden.plane[0], vden.line[0], 16, plane_st(vden, 0), tx, ty, tz, prt * 4);
+            rb = vm_group_f(vbl.plane[0], vbl.line[0], 16, plane_st(vden, 0), tx, ty, tz, prt * 4);
+            const float* pp = pw == 0 ? (sbl ? vbl.plane[1] : vden.plane[1]) : (sbl ? vbl.plane[2] : vden.plane[2]);
+            const float* ll = pw == 0 ? (sbl ? vbl.line[1] : vden.line[1]) : (sbl ? vbl.line[2] : vden.line[2]);
+            // plane 1: (u,v,l) = (x,z,y), W = Gx; plane 2: (y,z,x), W = Gy
+            rs = vm_group_f(pp, ll, 4, plane_st(vden, pw == 0 ? 1 : 2), pw == 0 ? tx : ty, tz, pw == 0 ? ty : tx, 0);
+          }
+#pragma unroll
+          for (int isbl = 0; isbl < 2; ++isbl) {
+            ring_wait_free(ring);
+            float* buf = ring_abuf(ring);
+            const int xrow = (isbl ? 152 : 80) + si * 24;   // XT rows: 80 position/time | 72 density | 72 blending
+            const float4 r = isbl ? rb : rd;
             store_quad(buf, m, prt, r);
             if (XT) store_quad_g(XT, ld, xrow + prt * 4, tile * kTileM + m, r);
-          }
-          if ((prt >> 1) == (isbl ? 1 : 0)) {   // the two 4-channel planes: threads 0,1 in density chunks, threads 2,3 in blending chunks
-            const int pw = prt & 1;
-            const float* pp = pw == 0 ? (isbl ? vbl.plane[1] : vden.plane[1]) : (isbl ? vbl.plane[2] : vden.plane[2]);
-            const float* ll = pw == 0 ? (isbl ? vbl.line[1] : vden.line[1]) : (isbl ? vbl.line[2] : vden.line[2]);
-            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-            // plane 1: (u,v,l) = (x,z,y), W = Gx; plane 2: (y,z,x), W = Gy
-            if (act)
-              r = vm_group_f(pp, ll, 4, plane_st(vden, pw == 0 ? 1 : 2), load_tap(taps, si, pw == 0 ? 0 : 1, m), load_tap(taps, si, 2, m),
-                             load_tap(taps, si, pw == 0 ? 1 : 0, m), 0);
-            store_quad(buf, m, 4 + pw, r);
-            if (XT) store_quad_g(XT, ld, xrow + 16 + pw * 4, tile * kTileM + m, r);
+            if (sbl == (isbl != 0)) {
+              store_quad(buf, m, 4 + pw, rs);
+              if (XT) store_quad_g(XT, ld, xrow + 16 + pw * 4, tile * kTileM + m, rs);
+            }
+            arrive();
           }
         }
-        umma::fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_full[ring.chunk % 3]);
-        ring.chunk++;
       }
-      // accumulators complete when the last chunk's commit lands (tcgen05 ops retire in order)
-      {
-        const uint32_t lc = ring.chunk - 1;
-        umma::mbar_wait(&bar_free[lc % 3], (lc / 3) & 1);
+      if (hasX) {
+        const SbScratch& scr = scrv[sx];
+        float* part = part0 + sx * (4 * kTileM);
+        const int tile = tileX;
+        umma::mbar_wait_backoff(&bar_stage[sx], (uint32_t)(((k - 1) >> 1) & 1));
         umma::fence_after_sync();
-      }
-      {
-        const int q = warp & 3, cb = warp >> 2;  // lane quadrant, 32-column block (0,1: density  2,3: blending)
-        float r[32];
-        umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + cb * 32, r);
-        float acc = 0.f;
-        const bool on = scr.on[q * 32 + lane] != 0;
+        {
+          const int q = warp & 3, cb = warp >> 2;  // lane quadrant, 32-column block (0,1: density  2,3: blending)
+          float r[32];
+          umma::tmem_ld32(ring.tmem + ((uint32_t)(q * 32) << 16) + sx * 128 + cb * 32, r);
+          float acc = 0.f;
+          const bool on = scr.on[q * 32 + lane] != 0;
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const int n = cb * 32 + jj;
-          r[jj] = fmaxf(r[jj] + cst[n], 0.f);
-          acc = fmaf(r[jj], cst[128 + n], acc);
-        }
-        part[cb * kTileM + q * 32 + lane] = acc;
-        if (HT) {   // hidden activations for the backward (zero on samples outside the bounding box)
+          for (int jj = 0; jj < 32; ++jj) {
+            const int n = cb * 32 + jj;
+            r[jj] = fmaxf(r[jj] + cst[n], 0.f);
+            acc = fmaf(r[jj], cst[128 + n], acc);
+          }
+          part[cb * kTileM + q * 32 + lane] = acc;
+          if (HT) {   // hidden activations for the backward (zero on samples outside the bounding box)
 #pragma unroll
-          for (int qq = 0; qq < 8; ++qq)
-            store_quad_g(HT, ld, cb * 32 + qq * 4, tile * kTileM + q * 32 + lane,
-                         on ? make_float4(r[qq * 4], r[qq * 4 + 1], r[qq * 4 + 2], r[qq * 4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f));
+            for (int qq = 0; qq < 8; ++qq)
+              store_quad_g(HT, ld, cb * 32 + qq * 4, tile * kTileM + q * 32 + lane,
+                           on ? make_float4(r[qq * 4], r[qq * 4 + 1], r[qq * 4 + 2], r[qq * 4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f));
+          }
         }
-      }
-      umma::fence_before_sync();
-      prod_bar();
-      if (tid < 2 * kTileM) {
-        const int which = tid >> 7, mm = tid & (kTileM - 1);
-        const int i = tile * kTileM + mm;
-        if (i < P) {
-          const bool v = scr.on[mm] != 0;
-          const float o = part[(2 * which) * kTileM + mm] + part[(2 * which + 1) * kTileM + mm] + __ldg(b2cat + which);
-          if (which == 0) sigma[i] = v ? density_act(o, cfg.act, cfg.density_shift) : 0.f;
-          else blend[i] = v ? sigmoidf_(o) : 0.f;
+        umma::fence_before_sync();
+        prod_bar();
+        if (tid < 2 * kTileM) {
+          const int which = tid >> 7, mm = tid & (kTileM - 1);
+          const int i = tile * kTileM + mm;
+          if (i < P) {
+            const bool v = scr.on[mm] != 0;
+            const float o = part[(2 * which) * kTileM + mm] + part[(2 * which + 1) * kTileM + mm] + __ldg(b2cat + which);
+            if (which == 0) sigma[i] = v ? density_act(o, cfg.act, cfg.density_shift) : 0.f;
+            else blend[i] = v ? sigmoidf_(o) : 0.f;
+          }
         }
+        prod_bar();
       }
-      prod_bar();
     }
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(ring.tmem, 128);
+  if (warp == 0) umma::tmem_dealloc(ring.tmem, 256);
 }
 
 // reference column of density/blending layer-1 for (chunk j, row k) of the K order above
