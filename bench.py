@@ -415,7 +415,7 @@ def main():
     # ---- per-kernel times for the roofline lines: EAGER steps of the SAME mode (the kernel variants the timed step runs),
     # CUDA events around each entry point on the launching stream, L2 flushed between steps
     names = ["dynrf_static_sigma_weight_fwd", "dynrf_dyn_sigma_blend_fwd_tc2", "dynrf_dyn_mlp_bwd_tc", "dynrf_basis_bwd",
-             "dynrf_head_bwd_tc", "dynrf_app_fwd_tc", "dynrf_warp_fwd_tc", "dynrf_warp_bwd", "dynrf_warp_bwd_tc", "dynrf_wgrad_gemm",
+             "dynrf_head_bwd_tc", "dynrf_app_fwd_tc", "dynrf_warp_fwd_tc", "dynrf_warp_fwd_tc2", "dynrf_warp_bwd", "dynrf_warp_bwd_tc", "dynrf_wgrad_gemm",
              "dynrf_static_density_bwd", "dynrf_composite_fwd", "dynrf_composite_bwd", "dynrf_alpha_weight_fwd",
              "dynrf_alpha_weight_bwd", "dynrf_sample_points", "dynrf_render_static_fwd", "dynrf_render_composite_fwd"]
     prof = TS.Step(static, dyn, N_SAMPLES, RT, mode, 1, graph=False, rays_grad=w["rays_grad"] and mode == "train")

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DYNRF_ABI_VERSION 2
+#define DYNRF_ABI_VERSION 3
 
 #define DYNRF_E_ARG (-1)         /* null pointer / non-positive size */
 #define DYNRF_E_UNSUPPORTED (-2) /* configuration outside the compiled kernels (component counts, widths) */
@@ -229,11 +229,12 @@ int dynrf_dyn_mlp_bwd(const dynrf_field_cfg_t* cfg, int mode, const dynrf_vm_t* 
                       const dynrf_layer_grad_t* g1, const dynrf_layer_grad_t* g2, float* gxp, void* stream);
 
 /* coordinate warp backward.  wb4 = pack_bwd(layer4.w,0,64,64 rows); wb3t = pack_bwd(layer3.w,63,93,64 rows).
- * gxp [N][S][3] = total d loss / d xyz_prime.  gtout [N][32] += d loss / d t_out (per ray). */
+ * gxp [N][S][3] = total d loss / d xyz_prime.  gtout [N][32] += d loss / d t_out (per ray).
+ * H1T / H2T [64][ld] (both or neither): relu(layer3), relu(layer4) as kept by dynrf_warp_fwd_tc; NULL = recompute them. */
 int dynrf_warp_bwd(const dynrf_field_cfg_t* cfg, const float* xyz, int N, int S, const float* tfeat, const dynrf_layer_t* l3,
                    const dynrf_layer_t* l4, const dynrf_layer_t* l5, const float* wb4, const float* wb3t, const float* gxp,
                    const dynrf_layer_grad_t* g3, const dynrf_layer_grad_t* g4, const dynrf_layer_grad_t* g5, float* gtout,
-                   void* stream);
+                   const float* H1T, const float* H2T, int ld, void* stream);
 
 /* time-embedding MLP backward: gtout [N][32] -> packed gradients of layer1 / layer2. */
 int dynrf_time_embed_bwd(const float* ts, int N, const dynrf_layer_t* l1, const dynrf_layer_t* l2, const float* gtout,
@@ -252,7 +253,16 @@ int dynrf_pack_linear_umma(const float* w, const float* bias_or_null, int N, int
 /* same contracts as dynrf_warp_fwd / dynrf_dyn_sigma_blend_fwd; 3-pass split-TF32 MMAs, fp32 accumulation in TMEM */
 int dynrf_warp_fwd_tc(const dynrf_field_cfg_t* cfg, const float* xyz, int N, int S, const float* tfeat,
                       const dynrf_umma_layer_t* layer3, const dynrf_umma_layer_t* layer4, const dynrf_layer_t* layer5,
-                      float* xyz_prime, void* stream);
+                      float* xyz_prime, float* H1T, float* H2T, int ld, void* stream);
+/* v2 of the tensor-core coordinate warp (models/tensoRF.py:521-541): warp-specialised, two tiles in flight.
+ * wq: dynrf_warp_fwd_wfloats() floats packed by dynrf_pack_warp_fwd from layer3.weight [64][93] and layer4.weight [64][64];
+ * cst: dynrf_warp_fwd_cst_floats() floats = layer3.bias (64) | layer4.bias (64) | layer5.weight^T [64][3] | layer5.bias (3).
+ * H1T / H2T [64][ld] (both or neither): relu(layer3) / relu(layer4) kept for dynrf_warp_bwd. */
+int dynrf_warp_fwd_wfloats(void);
+int dynrf_warp_fwd_cst_floats(void);
+int dynrf_pack_warp_fwd(const float* w3, const float* w4, float* wq, void* stream);
+int dynrf_warp_fwd_tc2(const dynrf_field_cfg_t* cfg, const float* wq, const float* cst, const float* xyz, int N, int S,
+                       const float* tfeat, float* xyz_prime, float* H1T, float* H2T, int ld, void* stream);
 int dynrf_dyn_sigma_blend_fwd_tc(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* density, const dynrf_vm_t* blending,
                                  const dynrf_umma_layer_t* d1, const dynrf_layer_t* d2, const dynrf_umma_layer_t* b1,
                                  const dynrf_layer_t* b2, const float* xyz, const float* xyz_prime, const uint8_t* valid,

@@ -12,6 +12,13 @@
 // register budget allows, otherwise flushed per tile.
 #include "dynrf_tile.cuh"
 
+// read-once activation streams: evict-first (see dynrf_tc.cuh)
+#ifdef DYNRF_STREAM_HINTS
+#define DYNRF_LD_STREAM_F(ptr) __ldcs(ptr)
+#else
+#define DYNRF_LD_STREAM_F(ptr) __ldg(ptr)
+#endif
+
 namespace dynrf {
 
 constexpr int kBT = 64;       // backward tile
@@ -397,7 +404,8 @@ constexpr size_t kWarpBwdSmem = (size_t)(96 * kBL + 64 * kBL + 64 * kBL + 2 * kC
 __global__ void __launch_bounds__(kMlpThreads, 2)
 k_warp_bwd(dynrf_field_cfg_t cfg, const float* __restrict__ xyz, int P, int S, const float* __restrict__ tfeat, dynrf_layer_t l3,
            dynrf_layer_t l4, dynrf_layer_t l5, const float* __restrict__ wb4 /*[64][64]*/, const float* __restrict__ wb3t /*[64][32]*/,
-           const float* __restrict__ gxp, LayerGrad g3, LayerGrad g4, LayerGrad g5, float* __restrict__ gtout) {
+           const float* __restrict__ gxp, LayerGrad g3, LayerGrad g4, LayerGrad g5, float* __restrict__ gtout,
+           const float* __restrict__ H1T /*[64][ld] relu(layer 3) kept by the forward, optional*/, const float* __restrict__ H2T, int ld) {
   extern __shared__ __align__(16) float smem[];
   float* A = smem;
   float* H1 = A + 96 * kBL;
@@ -429,8 +437,19 @@ k_warp_bwd(dynrf_field_cfg_t cfg, const float* __restrict__ xyz, int P, int S, c
     __syncthreads();
     fill_warp_rows<kBT, kBL>(scr, tfeat, A, tid);
     __syncthreads();
-    dense_tile<64, kBT, kBL, true>(A, l3, H1, wbuf, tid);
-    dense_tile<64, kBT, kBL, true>(H1, l4, H2, wbuf, tid);
+    if (H1T) {
+      // hidden activations kept by the forward kernel: 10 of the 26 kMAC per sample of this kernel were their recomputation
+      for (int e = tid; e < 64 * kBT; e += kMlpThreads) {
+        const int k = e / kBT, m = e % kBT;
+        const size_t src = (size_t)k * ld + (size_t)tile * kBT + m;
+        H1[(size_t)k * kBL + m] = DYNRF_LD_STREAM_F(H1T + src);
+        H2[(size_t)k * kBL + m] = DYNRF_LD_STREAM_F(H2T + src);
+      }
+      __syncthreads();
+    } else {
+      dense_tile<64, kBT, kBL, true>(A, l3, H1, wbuf, tid);
+      dense_tile<64, kBT, kBL, true>(H1, l4, H2, wbuf, tid);
+    }
     // layer5: dW5[k][o] += sum_m H2[k][m] g[o][m]; db5[o] += sum_m g[o][m]
     if (tid < 64) {
       const float* h = H2 + (size_t)tid * kBL;
@@ -968,14 +987,16 @@ int dynrf_static_density_bwd(const dynrf_field_cfg_t* cfg, const dynrf_vm_t* den
 int dynrf_warp_bwd(const dynrf_field_cfg_t* cfg, const float* xyz, int N, int S, const float* tfeat, const dynrf_layer_t* l3,
                    const dynrf_layer_t* l4, const dynrf_layer_t* l5, const float* wb4, const float* wb3t, const float* gxp,
                    const dynrf_layer_grad_t* g3, const dynrf_layer_grad_t* g4, const dynrf_layer_grad_t* g5, float* gtout,
-                   void* stream) {
+                   const float* H1T, const float* H2T, int ld, void* stream) {
   if (!cfg || !xyz || !tfeat || !l3 || !l4 || !l5 || !wb4 || !wb3t || !gxp || !g3 || !g4 || !g5 || !gtout || N <= 0 || S <= 0)
     return DYNRF_E_ARG;
+  if ((H1T != nullptr) != (H2T != nullptr)) return DYNRF_E_ARG;
+  if (H1T && ld < ((N * S + kBT - 1) / kBT) * kBT) return DYNRF_E_ARG;
   DYNRF_TRY(set_smem(k_warp_bwd, kWarpBwdSmem));
   const int P = N * S;
   const int grid = min((P + kBT - 1) / kBT, 2 * sm_count());
   k_warp_bwd<<<grid, kMlpThreads, kWarpBwdSmem, S_(stream)>>>(*cfg, xyz, P, S, tfeat, *l3, *l4, *l5, wb4, wb3t, gxp, LG(g3), LG(g4),
-                                                              LG(g5), gtout);
+                                                              LG(g5), gtout, H1T, H2T, ld);
   DYNRF_CHECK_LAUNCH();
   return 0;
 }

@@ -151,11 +151,18 @@ struct Ring {
   uint32_t wslot = kWSlotFloats;  // floats per weight slot
   uint32_t nbuf = 3;              // operand buffers
   uint32_t nw = 2;                // weight slots: chunk c's weights are requested while chunk c - (nw - 1) is being issued
+  // "the MMAs of chunk c have completed" is signalled on bar_free[c % nfree].  nfree == nbuf (default) ties the barrier to the
+  // operand buffer: correct only if every warp waits at every chunk, because a parity wait on a barrier that is two phases behind
+  // succeeds at once.  The kernels whose warps wait only for the chunks they write (two-tile kernels) use nfree = kNFull.
+  uint32_t nfree = 3;
 };
 
+// wait until the operand buffer of the current chunk is free, i.e. until chunk (c - nbuf) has been consumed
 __device__ __forceinline__ void ring_wait_free(const Ring& r) {
-  const uint32_t b = r.chunk % r.nbuf, u = r.chunk / r.nbuf;
-  if (u > 0) umma::mbar_wait_backoff(&r.bar_free[b], (u - 1) & 1);
+  if (r.chunk >= r.nbuf) {
+    const uint32_t pc = r.chunk - r.nbuf;
+    umma::mbar_wait_backoff(&r.bar_free[pc % r.nfree], (pc / r.nfree) & 1);
+  }
 }
 __device__ __forceinline__ float* ring_abuf(const Ring& r) { return r.abuf + (size_t)(r.chunk % r.nbuf) * kOpFloats; }
 
@@ -163,7 +170,7 @@ __device__ __forceinline__ float* ring_abuf(const Ring& r) { return r.abuf + (si
 __device__ __forceinline__ void ring_prefetch_w(const Ring& r, uint32_t c, const float* blob, uint32_t bytes) {
   if (c >= r.nw) {
     const uint32_t pc = c - r.nw;
-    umma::mbar_wait(&r.bar_free[pc % r.nbuf], (pc / r.nbuf) & 1);
+    umma::mbar_wait(&r.bar_free[pc % r.nfree], (pc / r.nfree) & 1);
   }
   const uint32_t slot = c % r.nw;
   mbar_expect_tx(&r.bar_w[slot], bytes);
@@ -190,7 +197,7 @@ __device__ __forceinline__ void ring_issue(const Ring& r, int rows, uint32_t col
       umma::mma_tf32(r.tmem + col0, da, db, idesc, (!first || ps > 0 || j > 0) ? 1u : 0u);
     }
   }
-  umma::commit(&r.bar_free[buf]);
+  umma::commit(&r.bar_free[c % r.nfree]);
 }
 
 // row 0..79 of the position/time operand block (this engine's K order, see tc_kernels.cu) -> index 0..79 in the
@@ -223,6 +230,9 @@ __device__ __forceinline__ float warp_col_reduce32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// number of "chunk written" mbarriers of the two-tile kernels (chunk c arrives on barrier c % kNFull): decoupled from the number
+// of operand buffers so that a warp which does not write a chunk need not wait for the chunk's buffer before arriving
+constexpr int kNFull = 8;
 constexpr int kProdThreads = 512;
 constexpr int kTc3Threads = kProdThreads + 32;
 

@@ -129,15 +129,15 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
   TapsSmem* tapsv = reinterpret_cast<TapsSmem*>(part0 + 2 * 4 * 3 * kTileM);
   FwdScratch* scrv = reinterpret_cast<FwdScratch*>(tapsv + 2);
   uint64_t* bars = reinterpret_cast<uint64_t*>(scrv + 2);
-  uint64_t* bar_free = bars;        // [3]
-  uint64_t* bar_w = bars + 3;       // [2]
-  uint64_t* bar_full = bars + 5;    // [3]
-  uint64_t* bar_stage = bars + 8;   // [2 contexts][3 GEMM groups: basis, L1, L2]
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* bar_free = bars;                    // [kNFull] chunk c is consumed: barrier c % kNFull (see dynrf_tc.cuh)
+  uint64_t* bar_w = bars + kNFull;              // [2]
+  uint64_t* bar_stage = bars + kNFull + 2;      // [2 contexts][3 GEMM groups: basis, L1, L2]
+  uint64_t* bar_full = bars + kNFull + 8;       // [kNFull] chunk c is written: barrier c % kNFull
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2 * kNFull + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < 5; ++i) umma::mbar_init(&bars[i], 1);
-    for (int i = 0; i < 3; ++i) umma::mbar_init(&bar_full[i], kProdThreads / 32);
+    for (int i = 0; i < kNFull + 2; ++i) umma::mbar_init(&bars[i], 1);
+    for (int i = 0; i < kNFull; ++i) umma::mbar_init(&bar_full[i], kProdThreads / 32);
     for (int i = 0; i < 6; ++i) umma::mbar_init(&bar_stage[i], 1);
     umma::fence_mbar_init();
   }
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  Ring ring{bar_free, bar_w, abuf, wbuf, 0u, *tslot};
+  Ring ring{bar_free, bar_w, abuf, wbuf, 0u, *tslot, (uint32_t)kWSlotFloats, 3u, 2u, (uint32_t)kNFull};
   const int count = *a.active_count;
   const int ntiles = (count + kTileM - 1) / kTileM;
   const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
       for (uint32_t c = 0; sq.valid(); ++c) {
         const int j = sq.j(), s = sq.s();
         ring.chunk = c;
-        umma::mbar_wait(&bar_full[c % 3], (c / 3) & 1);
+        umma::mbar_wait(&bar_full[c % kNFull], (c / kNFull) & 1);
         const uint32_t col = (uint32_t)(s * kAfCtxCols);
         if (j < AF::kNB) ring_issue<32>(ring, 24, col, j == 0);
         else if (j < AF::kNB + AF::kNL1) ring_issue<128>(ring, AF::rows(j), col + 32u, j == AF::kNB);
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
       umma::fence_before_sync();   // orders this warp's tcgen05.ld before the MMAs that follow the arrival
       umma::fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_full[ring.chunk % 3]);
+      if (lane == 0) mbar_arrive(&bar_full[ring.chunk % kNFull]);
       ring.chunk++;
     };
 
@@ -247,6 +247,8 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
         prod_bar();
         // ---- S1a(Y): basis operand chunks (stride si, third c): c = 0,1 halves of the 48-channel xy plane; c = 2 the two
         //      12-channel planes
+        // (issuing the lookups of the three chunks of a stride together -- 24-30 loads in flight per thread -- was measured and
+        //  lost 7 %: the 96-register budget of a 17-warp CTA turns the extra live values into spills)
         const bool act = scrY.on[m] != 0;
 #pragma unroll 1
         for (int j = 0; j < AF::kNB; ++j) {
@@ -292,8 +294,8 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
         for (int jj = 0; jj < 32; ++jj) r[jj] = on ? fmaxf(r[jj] + b1[cb * 32 + jj], 0.f) : 0.f;
 #pragma unroll 1
         for (int c4 = 0; c4 < 4; ++c4) {
-          ring_wait_free(ring);
           if (c4 == cb) {
+            ring_wait_free(ring);
             float* buf = ring_abuf(ring);
 #pragma unroll
             for (int qq = 0; qq < 8; ++qq) store_quad(buf, em, qq, make_float4(r[qq * 4], r[qq * 4 + 1], r[qq * 4 + 2], r[qq * 4 + 3]));
@@ -336,8 +338,8 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_app_fwd_tc(dynrf_field_cfg_t
           }
 #pragma unroll 1
           for (int c4 = 0; c4 < 4; ++c4) {
-            ring_wait_free(ring);
             if (c4 == cb) {
+              ring_wait_free(ring);
               float* buf = ring_abuf(ring);
               store_quad(buf, em, 0, make_float4(s1[0], s1[1], s1[2], s1[3]));
               store_quad(buf, em, 1, make_float4(s1[4], s1[5], s1[6], s1[7]));

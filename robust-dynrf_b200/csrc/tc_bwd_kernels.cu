@@ -154,15 +154,15 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
   float* go0 = part0 + 2 * 4 * 3 * kTileM;  // [2][3][128] d loss / d (pre-sigmoid output)
   BwdScratch* scrv = reinterpret_cast<BwdScratch*>(go0 + 2 * 3 * kTileM);
   uint64_t* bars = reinterpret_cast<uint64_t*>(scrv + 2);
-  uint64_t* bar_free = bars;       // [kHbBufs]
-  uint64_t* bar_w = bars + 3;      // [kHbSlots]
-  uint64_t* bar_full = bars + 7;   // [kHbBufs]
-  uint64_t* bar_stage = bars + 10; // [2 contexts][4 groups]
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* bar_free = bars;                   // [kNFull]: "chunk c is consumed" lives on barrier c % kNFull, not on the operand buffer's index
+  uint64_t* bar_w = bars + kNFull;             // [kHbSlots]
+  uint64_t* bar_stage = bars + kNFull + 3;     // [2 contexts][4 groups]
+  uint64_t* bar_full = bars + kNFull + 11;     // [kNFull]: "chunk c is written"
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 2 * kNFull + 11);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < 7; ++i) umma::mbar_init(&bars[i], 1);
-    for (int i = 0; i < 3; ++i) umma::mbar_init(&bar_full[i], kProdThreads / 32);
+    for (int i = 0; i < kNFull + 3; ++i) umma::mbar_init(&bars[i], 1);
+    for (int i = 0; i < kNFull; ++i) umma::mbar_init(&bar_full[i], kProdThreads / 32);
     for (int i = 0; i < 8; ++i) umma::mbar_init(&bar_stage[i], 1);
     umma::fence_mbar_init();
   }
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  Ring ring{bar_free, bar_w, abuf, wbuf, 0u, *tslot, (uint32_t)kHbWSlot, kHbBufs, kHbSlots};
+  Ring ring{bar_free, bar_w, abuf, wbuf, 0u, *tslot, (uint32_t)kHbWSlot, kHbBufs, kHbSlots, (uint32_t)kNFull};
   const int count = *a.active_count;
   const int ntiles = (count + kTileM - 1) / kTileM;
   const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
         const int j = cu.j(), s = cu.sq.ctx;
         const uint32_t col = (uint32_t)(s * kHbCtxCols);
         ring.chunk = c;
-        umma::mbar_wait(&bar_full[c % kHbBufs], (c / kHbBufs) & 1);
+        umma::mbar_wait(&bar_full[c % kNFull], (c / kNFull) & 1);
         if (j < kL2) ring_issue<128>(ring, HB::rows(j), col, j == 0);
         else if (j < kD2) ring_issue<128>(ring, 32, col + 128u, j == kL2);
         else if (j < kD1) ring_issue<128>(ring, 32, col + 128u, j == kD2);   // acc3 over acc2
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
       umma::fence_before_sync();   // orders this warp's tcgen05.ld before the MMAs that follow the arrival
       umma::fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_full[ring.chunk % kHbBufs]);
+      if (lane == 0) mbar_arrive(&bar_full[ring.chunk % kNFull]);
       ring.chunk++;
     };
 
@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
           }
 #pragma unroll 1
           for (int c4 = 0; c4 < 4; ++c4) {
-            ring_wait_free(ring);
             if (c4 == cb) {
+              ring_wait_free(ring);
               float* buf = ring_abuf(ring);
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
@@ -383,10 +383,11 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
         for (int jj = 0; jj < 32; ++jj) r[jj] = on ? fmaxf(r[jj] + b1[cb * 32 + jj], 0.f) : 0.f;
 #pragma unroll 1
         for (int c4 = 0; c4 < 4; ++c4) {
-          // every warp waits for the slot's previous use before arriving: an early arrival meant for chunk c would
-          // otherwise be counted in the still-open phase of an older chunk on the same barrier
-          ring_wait_free(ring);
+          // only the warps that write the chunk wait for its operand buffer; the others arrive at once (the "written" barriers
+          // are indexed by c % kNFull, so an early arrival cannot fall into the still-open phase of an older chunk: between two
+          // chunks kNFull apart every warp passes a CTA-wide barrier of the producers)
           if (c4 == cb) {
+            ring_wait_free(ring);
             float* buf = ring_abuf(ring);
 #pragma unroll
             for (int qq = 0; qq < 8; ++qq) {
@@ -458,8 +459,8 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
         }
 #pragma unroll 1
         for (int c4 = 0; c4 < 4; ++c4) {
-          ring_wait_free(ring);
           if (c4 == cb) {
+            ring_wait_free(ring);
             float* buf = ring_abuf(ring);
 #pragma unroll
             for (int qq = 0; qq < 8; ++qq) {
@@ -489,8 +490,8 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
         prod_bar();
 #pragma unroll 1
         for (int c4 = 0; c4 < 4; ++c4) {
-          ring_wait_free(ring);
           if (c4 == cb) {
+            ring_wait_free(ring);
             float* buf = ring_abuf(ring);
 #pragma unroll
             for (int qq = 0; qq < 8; ++qq) {
@@ -554,9 +555,15 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
     atomicAdd(a.gb2 + cb * 32 + lane, acc_b2);
     if (tid < kTileM) {
 #pragma unroll
-      for (int i = 0; i < 9; ++i) atomicAdd(a.gw3v + i, warp_sum(acc_vd[i]) * (lane == 0 ? 1.f : 0.f));
+      for (int i = 0; i < 9; ++i) {   // one reduction per warp: 32 same-address reductions per warp (31 of them adding zero) from
+        const float v = warp_sum(acc_vd[i]);   // every CTA at the end of the kernel serialised in L2 -- 9-14 % of the stall samples
+        if (lane == 0) atomicAdd(a.gw3v + i, v);   // sat at the closing barrier behind them
+      }
 #pragma unroll
-      for (int i = 0; i < 3; ++i) atomicAdd(a.gb3 + i, warp_sum(acc_b3[i]) * (lane == 0 ? 1.f : 0.f));
+      for (int i = 0; i < 3; ++i) {
+        const float v = warp_sum(acc_b3[i]);
+        if (lane == 0) atomicAdd(a.gb3 + i, v);
+      }
     }
   }
   umma::fence_before_sync();

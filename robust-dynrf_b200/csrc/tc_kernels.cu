@@ -215,7 +215,8 @@ constexpr size_t kWarpTcSmem =
 
 __global__ void __launch_bounds__(kMlpThreads)
 k_warp_tc(dynrf_field_cfg_t cfg, const float* __restrict__ xyz, int P, int S, const float* __restrict__ tfeat, UmmaLayer l3,
-          UmmaLayer l4, dynrf_layer_t l5, float* __restrict__ xyz_prime) {
+          UmmaLayer l4, dynrf_layer_t l5, float* __restrict__ xyz_prime, float* __restrict__ H1T /*[64][ld] optional*/,
+          float* __restrict__ H2T /*[64][ld] optional*/, int ld) {
   extern __shared__ __align__(128) float smem[];
   float* Sg = smem;
   float* a_hi = Sg + 96 * kTileM;
@@ -270,7 +271,9 @@ k_warp_tc(dynrf_field_cfg_t cfg, const float* __restrict__ xyz, int P, int S, co
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int n = cb * 32 + q * 4 + j;
-            umma::split_tf32(fmaxf(r[q * 4 + j] + __ldg(l3.bias + n), 0.f), hi[j], lo[j]);
+            const float h = fmaxf(r[q * 4 + j] + __ldg(l3.bias + n), 0.f);
+            umma::split_tf32(h, hi[j], lo[j]);
+            if (H1T) DYNRF_ST_STREAM(H1T + (size_t)n * ld + tile * kTileM + m, h);   // kept for the backward (k_warp_bwd)
           }
           const uint32_t off = umma::kmajor_off(m, cb * 32 + q * 4, kTileM) >> 2;
           *reinterpret_cast<float4*>(h_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
@@ -295,6 +298,7 @@ k_warp_tc(dynrf_field_cfg_t cfg, const float* __restrict__ xyz, int P, int S, co
         for (int j = 0; j < 32; ++j) {
           const int n = cb * 32 + j;
           const float h = fmaxf(r[j] + __ldg(l4.bias + n), 0.f);
+          if (H2T) DYNRF_ST_STREAM(H2T + (size_t)n * ld + tile * kTileM + m, h);
 #pragma unroll
           for (int o = 0; o < 3; ++o) d3[o] = fmaf(h, __ldg(l5.wt + (size_t)n * l5.Npad + o), d3[o]);
         }
@@ -681,8 +685,10 @@ int dynrf_dyn_sigma_blend_fwd_tc2(const dynrf_field_cfg_t* cfg, const dynrf_vm_t
 
 int dynrf_warp_fwd_tc(const dynrf_field_cfg_t* cfg, const float* xyz, int N, int S, const float* tfeat,
                       const dynrf_umma_layer_t* l3, const dynrf_umma_layer_t* l4, const dynrf_layer_t* l5, float* xyz_prime,
-                      void* stream) {
+                      float* H1T, float* H2T, int ld, void* stream) {
   if (!cfg || !xyz || !tfeat || !xyz_prime || !l5 || N <= 0 || S <= 0) return DYNRF_E_ARG;
+  if ((H1T != nullptr) != (H2T != nullptr)) return DYNRF_E_ARG;
+  if (H1T && ld < ((N * S + kTileM - 1) / kTileM) * kTileM) return DYNRF_E_ARG;
   DYNRF_TRY(check_ul(l3, 93, 64));
   DYNRF_TRY(check_ul(l4, 64, 64));
   if (l5->K != 64 || l5->N != 3) return DYNRF_E_UNSUPPORTED;
@@ -690,7 +696,7 @@ int dynrf_warp_fwd_tc(const dynrf_field_cfg_t* cfg, const float* xyz, int N, int
   if (e != cudaSuccess) return (int)e;
   const int P = N * S;
   const int grid = min((P + kTileM - 1) / kTileM, sm_count());
-  k_warp_tc<<<grid, kMlpThreads, kWarpTcSmem, S_(stream)>>>(*cfg, xyz, P, S, tfeat, UL(l3), UL(l4), *l5, xyz_prime);
+  k_warp_tc<<<grid, kMlpThreads, kWarpTcSmem, S_(stream)>>>(*cfg, xyz, P, S, tfeat, UL(l3), UL(l4), *l5, xyz_prime, H1T, H2T, ld);
   DYNRF_CHECK_LAUNCH();
   return 0;
 }

@@ -296,9 +296,12 @@ class DynamicFieldFn(torch.autograd.Function):
         gtout = arena.take(n, 32)
         wb4 = pack_bwd(pk["layer4"], 0, 64, 64)
         wb3t = pack_bwd(pk["layer3"], 63, 93, 64)
+        wsv = r.get("warp_saved")
         L.check(lib.dynrf_warp_bwd(C.byref(cfg), _p(r["xyz"]), n, s, _p(r["tfeat"]), C.byref(ly["layer3"]), C.byref(ly["layer4"]),
                                    C.byref(ly["layer5"]), _p(wb4), _p(wb3t), _p(gxp), C.byref(gl["layer3"].struct),
-                                   C.byref(gl["layer4"].struct), C.byref(gl["layer5"].struct), _p(gtout), _stream()),
+                                   C.byref(gl["layer4"].struct), C.byref(gl["layer5"].struct), _p(gtout),
+                                   _p(wsv[:64]) if wsv is not None else None, _p(wsv[64:]) if wsv is not None else None,
+                                   r.get("warp_ld", 0), _stream()),
                 "dynrf_warp_bwd")
         L.check(lib.dynrf_time_embed_bwd(_p(r["ts"]), n, C.byref(ly["layer1"]), C.byref(ly["layer2"]), _p(gtout),
                                          C.byref(gl["layer1"].struct), C.byref(gl["layer2"].struct), _stream()),

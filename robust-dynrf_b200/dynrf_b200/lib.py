@@ -16,7 +16,7 @@ LIB_DIR = os.path.join(PKG_ROOT, "lib")
 # DYNRF_VARIANT=<name> + DYNRF_NVCC_DEFS="-DFOO -DBAR": an experimental build next to the product library (A/B measurements)
 _VARIANT = os.environ.get("DYNRF_VARIANT", "")
 LIB_PATH = os.path.join(LIB_DIR, f"libdynrf_b200{'_' + _VARIANT if _VARIANT else ''}.so")
-SOURCES = ["ray_kernels.cu", "field_kernels.cu", "backward_kernels.cu", "tc_kernels.cu", "wgrad_gemm.cu", "tc_bwd_kernels.cu", "tc_sb_bwd.cu", "tc_app_fwd.cu", "extras_kernels.cu", "optim_kernels.cu"]
+SOURCES = ["ray_kernels.cu", "field_kernels.cu", "backward_kernels.cu", "tc_kernels.cu", "wgrad_gemm.cu", "tc_bwd_kernels.cu", "tc_sb_bwd.cu", "tc_app_fwd.cu", "tc_warp_fwd.cu", "extras_kernels.cu", "optim_kernels.cu"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -114,7 +114,7 @@ PROTOTYPES = {
     "dynrf_dyn_app_bwd": [_cfg, _vm, _vg, _ly, _ly, _ly, _ly, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _lg, _lg, _lg,
                           _lg, _P, _P],
     "dynrf_dyn_mlp_bwd": [_cfg, _I, _vm, _vg, _ly, _ly, _P, _P, _P, _P, _P, _I, _I, _P, _lg, _lg, _P, _P],
-    "dynrf_warp_bwd": [_cfg, _P, _I, _I, _P, _ly, _ly, _ly, _P, _P, _P, _lg, _lg, _lg, _P, _P],
+    "dynrf_warp_bwd": [_cfg, _P, _I, _I, _P, _ly, _ly, _ly, _P, _P, _P, _lg, _lg, _lg, _P, _P, _P, _I, _P],
     "dynrf_time_embed_bwd": [_P, _I, _ly, _ly, _P, _lg, _lg, _P],
     "dynrf_head_bwd_wfloats": [_I],
     "dynrf_head_bwd_xrows": [_I],
@@ -132,9 +132,13 @@ PROTOTYPES = {
     "dynrf_wgrad_gemm": [_P, _I, _I, _P, _I, _I, _I, _P, _P, _I, _P],
     "dynrf_pack_linear_umma": [_P, _P, _I, _I, _P, _P, _P],
     "dynrf_sb_umma_floats": [],
+    "dynrf_warp_fwd_wfloats": [],
+    "dynrf_warp_fwd_cst_floats": [],
+    "dynrf_pack_warp_fwd": [_P, _P, _P, _P],
+    "dynrf_warp_fwd_tc2": [_cfg, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P],
     "dynrf_pack_sb_umma": [_P, _P, _P, _P],
     "dynrf_dyn_sigma_blend_fwd_tc2": [_cfg, _vm, _vm, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P],
-    "dynrf_warp_fwd_tc": [_cfg, _P, _I, _I, _P, _ul, _ul, _ly, _P, _P],
+    "dynrf_warp_fwd_tc": [_cfg, _P, _I, _I, _P, _ul, _ul, _ly, _P, _P, _P, _I, _P],
     # rows next to the path (a4, f1-f3)
     "dynrf_sample_ray": [_cfg, _P, _I, _I, _F, _P, _P, _P, _P, _P],
     "dynrf_raygen_fwd": [_P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _F, _P, _P],
@@ -149,7 +153,7 @@ PROTOTYPES = {
 }
 
 _lib = None
-_NO_LAUNCH = {"dynrf_abi_version", "dynrf_pad_k", "dynrf_pad_n", "dynrf_strerror", "dynrf_sb_umma_floats", "dynrf_head_bwd_wfloats", "dynrf_head_bwd_cst_floats", "dynrf_head_bwd_xrows", "dynrf_sb_bwd_wfloats", "dynrf_app_fwd_wfloats", "dynrf_app_fwd_cst_floats", "dynrf_adam_blocks"}
+_NO_LAUNCH = {"dynrf_abi_version", "dynrf_pad_k", "dynrf_pad_n", "dynrf_strerror", "dynrf_sb_umma_floats", "dynrf_warp_fwd_wfloats", "dynrf_warp_fwd_cst_floats", "dynrf_head_bwd_wfloats", "dynrf_head_bwd_cst_floats", "dynrf_head_bwd_xrows", "dynrf_sb_bwd_wfloats", "dynrf_app_fwd_wfloats", "dynrf_app_fwd_cst_floats", "dynrf_adam_blocks"}
 
 # every other entry point enqueues exactly one kernel of this library; bench.py reports the count
 launch_count = 0

@@ -188,6 +188,7 @@ PARAM_EPOCH = [0]
 # keep layer inputs / hidden activations of the tensor-core forward kernels for their backward instead of recomputing them
 SAVE_ACTIVATIONS = True
 TC_SB_VERSION = 2
+TC_WARP_VERSION = int(os.environ.get("DYNRF_TC_WARP", "2"))   # 2: warp-specialised two-tile kernel (tc_warp_fwd.cu); 1: first-generation k_warp_tc (kept as a cross-check)
 
 
 def umma_layers(m, names):
@@ -227,6 +228,33 @@ class PackedSigmaBlend:
                 torch.cat((ps[1].detach(), ps[5].detach()), out=self.b1cat)
                 torch.cat((ps[2].detach().reshape(-1), ps[6].detach().reshape(-1)), out=self.w2cat)
                 torch.cat((ps[3].detach().reshape(-1), ps[7].detach().reshape(-1)), out=self.b2cat)
+            self._key = key
+        return self
+
+
+class PackedWarpFwd:
+    """Operands of dynrf_warp_fwd_tc2 (coordinate-warp MLP layer3 / layer4 / layer5), rebuilt when one of the layers changes."""
+
+    def __init__(self, m):
+        self.m = m
+        lib = L.load()
+        dev = m.layer3.weight.device
+        if tuple(m.layer3.weight.shape) != (64, 93) or tuple(m.layer4.weight.shape) != (64, 64) or tuple(m.layer5.weight.shape) != (3, 64):
+            raise NotImplementedError("tensor-core warp MLP is compiled for 93 -> 64 -> 64 -> 3 (models/tensoRF.py:521-541); got "
+                                      f"{tuple(m.layer3.weight.shape)}, {tuple(m.layer4.weight.shape)}, {tuple(m.layer5.weight.shape)}")
+        self.wq = torch.empty(lib.dynrf_warp_fwd_wfloats(), device=dev)
+        self.cst = torch.empty(lib.dynrf_warp_fwd_cst_floats(), device=dev)
+        self._key = None
+
+    def refresh(self):
+        m = self.m
+        ps = [m.layer3.weight, m.layer3.bias, m.layer4.weight, m.layer4.bias, m.layer5.weight, m.layer5.bias]
+        key = (PARAM_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self._key:
+            with torch.no_grad():
+                L.check(L.load().dynrf_pack_warp_fwd(_p(_f32c(ps[0].detach())), _p(_f32c(ps[2].detach())), _p(self.wq), _stream()),
+                        "dynrf_pack_warp_fwd")
+                torch.cat((ps[1].detach(), ps[3].detach(), ps[4].detach().t().reshape(-1), ps[5].detach()), out=self.cst)   # b3 | b4 | W5 [64][3] | b5
             self._key = key
         return self
 
@@ -438,10 +466,26 @@ def dynamic_forward_raw(m, rays, ts, xyz, z_vals, valid, ray_type, save_feat=Fal
     vden = vm_struct(m.density_plane, m.density_line)
     vbl = vm_struct(m.blending_plane, m.blending_line)
     sb_saved, sb_ld = None, 0
+    warp_saved, warp_ld = None, 0
     if USE_TC:
         ul = umma_layers(m, ("layer3", "layer4", "d1", "b1"))
-        L.check(lib.dynrf_warp_fwd_tc(C.byref(cfg), _p(xyz), n, s, _p(tfeat), C.byref(ul["layer3"]), C.byref(ul["layer4"]),
-                                      C.byref(ly["layer5"]), _p(xyz_prime), _stream()), "dynrf_warp_fwd_tc")
+        if save_feat and SAVE_ACTIVATIONS:
+            # hidden activations of the warp MLP, kept for k_warp_bwd (their recomputation was 10 of its 26 kMAC per sample);
+            # one [128][ld] block per forward call, owned by that call's record like the other saved activations
+            warp_ld = round_up(n * s, 128)
+            warp_saved = torch.empty(128, warp_ld, device=dev)
+        h1t = _p(warp_saved[:64]) if warp_saved is not None else None
+        h2t = _p(warp_saved[64:]) if warp_saved is not None else None
+        if TC_WARP_VERSION == 2:
+            pw = m.__dict__.get("_packed_warp")
+            if pw is None:
+                pw = m.__dict__["_packed_warp"] = PackedWarpFwd(m)
+            pw.refresh()
+            L.check(lib.dynrf_warp_fwd_tc2(C.byref(cfg), _p(pw.wq), _p(pw.cst), _p(xyz), n, s, _p(tfeat), _p(xyz_prime), h1t, h2t, warp_ld,
+                                           _stream()), "dynrf_warp_fwd_tc2")
+        else:
+            L.check(lib.dynrf_warp_fwd_tc(C.byref(cfg), _p(xyz), n, s, _p(tfeat), C.byref(ul["layer3"]), C.byref(ul["layer4"]),
+                                          C.byref(ly["layer5"]), _p(xyz_prime), h1t, h2t, warp_ld, _stream()), "dynrf_warp_fwd_tc")
         if TC_SB_VERSION == 2:
             psb = m.__dict__.get("_packed_sb")
             if psb is None:
@@ -488,7 +532,8 @@ def dynamic_forward_raw(m, rays, ts, xyz, z_vals, valid, ray_type, save_feat=Fal
                                       C.byref(ly["h3"]), _p(rays), _p(xyz), _p(xyz_prime), _p(tfeat), n, s, _p(idx), _p(cnt),
                                       _p(rgb), _p(featT), ldf, _stream()), "dynrf_dyn_app_fwd")
     return dict(sigma=sigma, blend=blend, weight=weight, dists=dists, rgb=rgb, xyz_prime=xyz_prime, tfeat=tfeat, idx=idx,
-                cnt=cnt, rays=rays, ts=ts, xyz=xyz, z_vals=z_vals, valid=valid_u8, featT=featT, ldf=ldf, sb_saved=sb_saved, sb_ld=sb_ld)
+                cnt=cnt, rays=rays, ts=ts, xyz=xyz, z_vals=z_vals, valid=valid_u8, featT=featT, ldf=ldf, sb_saved=sb_saved, sb_ld=sb_ld,
+                warp_saved=warp_saved, warp_ld=warp_ld)
 
 
 def composite_raw(rgb_s, sigma_s, rgb_d, sigma_d, dists, blending, z_vals, rays, white_bg: bool, ray_type: str):

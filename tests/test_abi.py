@@ -23,7 +23,7 @@ def test_build_and_symbols():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/dynrf_b200.h but not exported"
     assert sorted(set(L.PROTOTYPES) | {"dynrf_strerror"}) == declared
-    assert lib.dynrf_abi_version() == 2   # v2: dynrf_vm_t carries the texel strides sv / su
+    assert lib.dynrf_abi_version() == 3   # v2: dynrf_vm_t texel strides sv / su; v3: warp-MLP hidden activations kept for the backward
     assert lib.dynrf_pad_k(93) == 96 and lib.dynrf_pad_n(27) == 32
     assert b"argument" in lib.dynrf_strerror(-1)
 
