@@ -485,7 +485,7 @@ def main():
         ksum = sum(kms.values())
         dom_kernel = {"dynrf_dyn_mlp_bwd_tc": "k_dyn_mlp_bwd_tc<1>", "dynrf_basis_bwd": "k_basis_bwd<1>", "dynrf_head_bwd_tc": "k_head_bwd_tc<0>",
                       "dynrf_dyn_sigma_blend_fwd_tc2": "k_dyn_sigma_blend_tc2", "dynrf_app_fwd_tc": "k_app_fwd_tc<1>",
-                      "dynrf_warp_bwd": "k_warp_bwd", "dynrf_warp_bwd_tc": "k_warp_bwd_tc"}.get(dom_name, dom_name)
+                      "dynrf_warp_bwd": "k_warp_bwd", "dynrf_warp_bwd_tc": "k_warp_bwd_tc", "dynrf_warp_fwd_tc2": "k_warp_fwd_tc2"}.get(dom_name, dom_name)
         dom_traffic, dom_meas = traffic_of(dom_kernel) if dom_name else (None, None)
         dom_ms_launch = (dom_ms / klaunch[dom_name]) if dom_name else None
         dom_row = (ktab.get("kernels") or {}).get(dom_kernel) or {}

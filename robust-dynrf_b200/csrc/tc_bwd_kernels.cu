@@ -650,8 +650,11 @@ constexpr int kBL2 = kBT2 + 4;
 using BScratch2 = TileScratch<kBT2>;
 constexpr size_t kBasisBwdSmem = (size_t)((72 + 32 + 80) * kBL2 + 2 * kChunkK * 80) * sizeof(float) + sizeof(BScratch2);
 
+#ifndef DYNRF_BASIS_CTAS
+#define DYNRF_BASIS_CTAS 2   // CTAs per SM the kernel is compiled for (3: 80 registers + ~300 B of spills per thread, 24 warps per SM)
+#endif
 template <bool DYN>
-__global__ void __launch_bounds__(kMlpThreads, 2)
+__global__ void __launch_bounds__(kMlpThreads, DYNRF_BASIS_CTAS)
 k_basis_bwd(dynrf_field_cfg_t cfg, dynrf_vm_t vm, dynrf_vm_grad_t gvm, const float* __restrict__ wbB /*[nstr][32][80]*/,
             const float* __restrict__ coords /*xyz_prime (DYN) | xyz*/, const float* __restrict__ DFT, int ld,
             const int32_t* __restrict__ active_idx, const int32_t* __restrict__ active_count, float* __restrict__ gbasis_wt /*[K][32]*/,
@@ -778,7 +781,7 @@ int dynrf_basis_bwd(const dynrf_field_cfg_t* cfg, int dynamic, const dynrf_vm_t*
   if (app->W[1] != app->W[0] || app->W[2] != app->H[0] || app->H[1] != app->L[0] || app->H[2] != app->L[0] || app->L[1] != app->H[0] ||
       app->L[2] != app->W[0])
     return DYNRF_E_UNSUPPORTED;
-  const int grid = min((N * S + kBT2 - 1) / kBT2, 2 * sm_count());
+  const int grid = min((N * S + kBT2 - 1) / kBT2, DYNRF_BASIS_CTAS * sm_count());
   cudaError_t e;
   if (dynamic) {
     e = cudaFuncSetAttribute(k_basis_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBasisBwdSmem);

@@ -336,3 +336,43 @@ def test_tc_pack_rejects_unsupported_hyperparameters():
         R.raw2outputs(torch.zeros(4, 8, 3, device=dev), torch.zeros(4, 8, device=dev), torch.zeros(4, 8, 3, device=dev),
                       torch.zeros(4, 8, device=dev), torch.zeros(4, 8, device=dev), torch.zeros(4, 8, device=dev),
                       torch.zeros(4, 8, device=dev), torch.zeros(4, 7, device=dev))
+
+
+@gpu
+def test_saved_activations_match_recompute():
+    """The backward reads the hidden activations the forward kept (density / blending layer 1, warp MLP layers 3, 4) or recomputes
+    them (ops.SAVE_ACTIVATIONS = False): same parameter gradients either way (the kept values come from the tensor-core forward,
+    the recomputed ones from the fp32 SIMT / tensor-core backward: a ReLU at ~1e-7 may flip, hence the kink-tolerant gate)."""
+    from dynrf_b200 import ops
+
+    case = H.build_pair([26, 30, 22], 160, 70, ray_type="ndc", static_mode="MLP_Fea", seed=77)
+    grads = []
+    try:
+        for keep in (True, False):
+            ops.SAVE_ACTIVATIONS = keep
+            static, dyn, _, fs, fd, o = _native_full(case)
+            ws = _loss_weights([t.shape for t in o] + [fd[5].shape, fd[2].shape], 5)
+            loss = sum((t * w.to(DEV)).sum() for t, w in zip(list(o) + [fd[5], fd[2]], ws))
+            loss.backward()
+            torch.cuda.synchronize()
+            grads.append({n: p.grad.detach().cpu().clone() for n, p in dyn.named_parameters() if p.grad is not None})
+    finally:
+        ops.SAVE_ACTIVATIONS = True
+    bad = {}
+    for n, g in grads[0].items():
+        ok, emax, rel2 = _grad_ok(g, grads[1][n], n_samples=160 * 70)
+        if not ok:
+            bad[n] = (emax, rel2)
+    assert not bad, bad
+
+
+@gpu
+@pytest.mark.parametrize("n,s", [(1, 16), (3, 43), (5, 128), (9, 129), (300, 64)])
+def test_two_tile_pipelines_tile_counts(n, s):
+    """The tile kernels keep two tiles in flight per CTA (prologue / epilogue of the software pipeline, odd tile counts, CTAs with
+    zero or one tile, a partial last tile): forward parity with the oracle and one backward for P = n * s from 16 to 19200."""
+    case = H.build_pair([18, 20, 17], n, s, ray_type="ndc", static_mode="MLP_Fea", seed=100 + n)
+    rep = H.compare_pass(H.oracle_pass(case), H.native_pass(case, DEV))
+    print(rep)
+    if n * s <= 2000:
+        _check_parameter_gradients(case)

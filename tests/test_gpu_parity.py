@@ -162,3 +162,22 @@ def test_softplus_density_activation(ray_type):
                         seed=31, act="softplus", density_shift=-1.5)
     rep = H.compare_pass(H.oracle_pass(case), H.native_pass(case, DEV))
     print(rep)
+
+
+@gpu
+def test_warp_forward_versions_agree():
+    """k_warp_fwd_tc2 (warp-specialised, two tiles in flight, own K order) vs the first-generation k_warp_tc: same xyz_prime."""
+    from dynrf_b200 import ops
+
+    case = H.build_pair([33, 29, 31], 260, 90, seed=12)
+    models = H.native_models(case, DEV)
+    try:
+        ops.TC_WARP_VERSION = 2
+        a = H.native_pass(case, DEV, models)
+        ops.TC_WARP_VERSION = 1
+        b = H.native_pass(case, DEV, models)
+    finally:
+        ops.TC_WARP_VERSION = 2
+    d = float((a["fd"][5] - b["fd"][5]).abs().max())
+    print("xyz_prime", d)
+    assert d <= 2e-6, d
