@@ -98,40 +98,60 @@ struct BwdScratch {
   int ray[kTileM], idx[kTileM], on[kTileM];
 };
 
+// Stage sequence of a CTA.  Per context the stages of a tile are  ES = [E4 of the context's PREVIOUS tile] + [S of this tile],
+// E1, E2, E3 -- E4 (the read-back of the last GEMM group, short for the dynamic head) is merged with the next tile's S so that every
+// slot of the alternation is a long stage: with E4 as a slot of its own, the GEMM group submitted by the stage before it had only
+// that short slot to complete in, and the following read-back waited (10.8 % + 9.4 % of the stall samples of the 5-stage schedule).
+// Contexts alternate strictly, B two stages behind A:  ES(A) . E1(A) . E2(A) ES(B) E3(A) E1(B) ES(A') E2(B) E1(A') E3(B) ...
 struct HeadStageSeq {
   int T, step, st0, st1, tl0, tl1;   // scalars (no indexed arrays: they would live in local memory)
-  int ctx, stage, tile;   // the stage to execute now: context, stage 0..4, tile ordinal (of this CTA) it belongs to
+  bool fin0, fin1;
+  int ctx, stage, tile;   // the stage to execute now: context, stage 0..3, tile ordinal (of this CTA) of its S / E1..E3 part
+  bool do_e4, do_s;       // stage 0: read back tile - 2 of the context / start tile `tile`
   __device__ __forceinline__ void init(int T_) {
     T = T_;
     step = -1;
     st0 = st1 = 0;
     tl0 = 0;
     tl1 = 1;
+    fin0 = fin1 = false;
   }
   // advance to the next executed stage; false when every tile of the CTA is finished
   __device__ __forceinline__ bool next() {
     for (;;) {
-      if (tl0 >= T && tl1 >= T) return false;
+      if (fin0 && fin1) return false;
       ++step;
       const int c = step & 1;
-      if (c == 1 && step < 5) continue;   // context B starts two and a half stages behind A
-      if ((c ? tl1 : tl0) >= T) continue;
+      if (c == 1 && step < 5) continue;   // context B starts two stages behind A
+      if (c ? fin1 : fin0) continue;
+      const int st = c ? st1 : st0, tl = c ? tl1 : tl0;
       ctx = c;
-      if (c) {
-        stage = st1;
-        tile = tl1;
-        if (++st1 == 5) {
-          st1 = 0;
-          tl1 += 2;
-        }
+      stage = st;
+      tile = tl;
+      int nst = st, ntl = tl;
+      bool fin = false;
+      if (st == 0) {
+        do_e4 = tl >= 2;
+        do_s = tl < T;
+        fin = !do_s;
+        if (do_s) nst = 1;
       } else {
-        stage = st0;
-        tile = tl0;
-        if (++st0 == 5) {
-          st0 = 0;
-          tl0 += 2;
+        do_e4 = do_s = false;
+        if (++nst == 4) {
+          nst = 0;
+          ntl = tl + 2;
         }
       }
+      if (c) {
+        st1 = nst;
+        tl1 = ntl;
+        fin1 = fin;
+      } else {
+        st0 = nst;
+        tl0 = ntl;
+        fin0 = fin;
+      }
+      if (st == 0 && !do_e4 && !do_s) continue;   // a context without tiles
       return true;
     }
   }
@@ -190,7 +210,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
         int i, n, j0;
         bool ok;
         __device__ __forceinline__ void load() {   // first chunk / chunk count of the current stage
-          n = sq.stage == 0 ? HB::kNL1 : (sq.stage == 4 ? 0 : 4);
+          n = sq.stage == 0 ? (sq.do_s ? HB::kNL1 : 0) : 4;
           j0 = sq.stage == 0 ? 0 : HB::kNL1 + 4 * (sq.stage - 1);
         }
         __device__ __forceinline__ void start(int T) {
@@ -273,7 +293,56 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
       const uint32_t tcol = ring.tmem + (uint32_t)(s * kHbCtxCols) + ((uint32_t)(q * 32) << 16);
       const uint32_t par = (uint32_t)((sq.tile >> 1) & 1);
       const int jg0 = ((int)blockIdx.x + sq.tile * (int)gridDim.x) * kTileM;
-      if (sq.stage == 0) {
+      if (sq.stage == 0 && sq.do_e4) {
+        // ---- epilogue 4 of the context's previous tile (tile - 2): dfeat
+        const uint32_t par4 = (uint32_t)(((sq.tile - 2) >> 1) & 1);
+        const int jg4 = ((int)blockIdx.x + (sq.tile - 2) * (int)gridDim.x) * kTileM;
+        umma::mbar_wait_backoff(&bar_stage[s * 4 + 3], par4);
+        umma::fence_after_sync();
+        if (DYN) {
+          if (cb == 0) {
+            float r4[32];
+            umma::tmem_ld32(tcol, r4);
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+              float4 v = make_float4(r4[qq * 4], r4[qq * 4 + 1], r4[qq * 4 + 2], r4[qq * 4 + 3]);
+              if (qq == 6) v.w = 0.f;            // only 27 feature rows carry a gradient
+              if (qq == 7) v = make_float4(0.f, 0.f, 0.f, 0.f);
+              store_quad_g(a.DFT, ld, qq * 4, jg4 + em, v);
+            }
+          }
+        } else {
+          // dX columns: [32 cb, 32 cb + 32) = d(sin f, sin 2f, cos f, cos 2f) of this thread's 8 features, [128 + 8 cb, +8) = d f
+          float dx[32], df[8];
+          umma::tmem_ld32(tcol + cb * 32, dx);
+          tmem_ld8_(tcol + 128 + cb * 8, df);
+          const bool on = scr.on[em] != 0;
+          if (cb == 3 && on && a.gvd) {
+            const int ry = scr.ray[em];
+            atomicAdd(a.gvd + (size_t)ry * 3 + 0, df[3]);
+            atomicAdd(a.gvd + (size_t)ry * 3 + 1, df[4]);
+            atomicAdd(a.gvd + (size_t)ry * 3 + 2, df[5]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float fi = on ? __ldg(a.featT + (size_t)(cb * 8 + i) * ld + jg4 + em) : 0.f;   // the basis output again (L2 hit)
+            float s1, c1, s2, c2;
+            sincosf(fi, &s1, &c1);
+            sincosf(fi * 2.0f, &s2, &c2);
+            // d/df [sin f, sin 2f, cos f, cos 2f] = [cos f, 2 cos 2f, -sin f, -2 sin 2f]
+            float g = df[i];
+            g = fmaf(dx[i], c1, g);
+            g = fmaf(dx[8 + i], 2.0f * c2, g);
+            g = fmaf(dx[16 + i], -s1, g);
+            g = fmaf(dx[24 + i], -2.0f * s2, g);
+            df[i] = (on && cb * 8 + i < 27) ? g : 0.f;
+          }
+          store_quad_g(a.DFT, ld, cb * 8, jg4 + em, make_float4(df[0], df[1], df[2], df[3]));
+          store_quad_g(a.DFT, ld, cb * 8 + 4, jg4 + em, make_float4(df[4], df[5], df[6], df[7]));
+        }
+        umma::fence_before_sync();
+      }
+      if (sq.stage == 0 && sq.do_s) {
         prod_bar();   // every warp is done with this context's scratch (E4 of its previous tile)
         if (tid < kTileM) {
           const int jg = jg0 + tid;
@@ -502,52 +571,6 @@ __global__ void __launch_bounds__(kTc3Threads, 1) k_head_bwd_tc(dynrf_field_cfg_
           }
           arrive();
         }
-      } else {
-        // ---- epilogue 4: dfeat
-        umma::mbar_wait_backoff(&bar_stage[s * 4 + 3], par);
-        umma::fence_after_sync();
-        if (DYN) {
-          if (cb == 0) {
-            float r4[32];
-            umma::tmem_ld32(tcol, r4);
-#pragma unroll
-            for (int qq = 0; qq < 8; ++qq) {
-              float4 v = make_float4(r4[qq * 4], r4[qq * 4 + 1], r4[qq * 4 + 2], r4[qq * 4 + 3]);
-              if (qq == 6) v.w = 0.f;            // only 27 feature rows carry a gradient
-              if (qq == 7) v = make_float4(0.f, 0.f, 0.f, 0.f);
-              store_quad_g(a.DFT, ld, qq * 4, jg0 + em, v);
-            }
-          }
-        } else {
-          // dX columns: [32 cb, 32 cb + 32) = d(sin f, sin 2f, cos f, cos 2f) of this thread's 8 features, [128 + 8 cb, +8) = d f
-          float dx[32], df[8];
-          umma::tmem_ld32(tcol + cb * 32, dx);
-          tmem_ld8_(tcol + 128 + cb * 8, df);
-          const bool on = scr.on[em] != 0;
-          if (cb == 3 && on && a.gvd) {
-            const int ry = scr.ray[em];
-            atomicAdd(a.gvd + (size_t)ry * 3 + 0, df[3]);
-            atomicAdd(a.gvd + (size_t)ry * 3 + 1, df[4]);
-            atomicAdd(a.gvd + (size_t)ry * 3 + 2, df[5]);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float fi = on ? __ldg(a.featT + (size_t)(cb * 8 + i) * ld + jg0 + em) : 0.f;   // the basis output again (L2 hit)
-            float s1, c1, s2, c2;
-            sincosf(fi, &s1, &c1);
-            sincosf(fi * 2.0f, &s2, &c2);
-            // d/df [sin f, sin 2f, cos f, cos 2f] = [cos f, 2 cos 2f, -sin f, -2 sin 2f]
-            float g = df[i];
-            g = fmaf(dx[i], c1, g);
-            g = fmaf(dx[8 + i], 2.0f * c2, g);
-            g = fmaf(dx[16 + i], -s1, g);
-            g = fmaf(dx[24 + i], -2.0f * s2, g);
-            df[i] = (on && cb * 8 + i < 27) ? g : 0.f;
-          }
-          store_quad_g(a.DFT, ld, cb * 8, jg0 + em, make_float4(df[0], df[1], df[2], df[3]));
-          store_quad_g(a.DFT, ld, cb * 8 + 4, jg0 + em, make_float4(df[4], df[5], df[6], df[7]));
-        }
-        umma::fence_before_sync();
       }
     }
 #pragma unroll
