@@ -83,10 +83,11 @@ constexpr uint32_t kHbBufs = 2, kHbSlots = 3;
 // A tile is a chain of four dependent GEMM groups (L1 -> L2 -> dH1 -> dX) with an epilogue between each pair; with one tile per
 // CTA the 16 producer warps spent 32 % of their stall samples at the group-completion mbarriers and 21 % at the barriers behind
 // them, while the tensor core idled during every epilogue.  The CTA therefore runs TWO tiles (contexts A, B; tiles dealt
-// alternately) through the five stages  S (scratch + L1 operand), E1, E2, E3, E4  in strict alternation, B half a tile behind A:
-//     S(A) . E1(A) . E2(A) S(B) E3(A) E1(B) E4(A) E2(B) S(A') E3(B) E1(A') E4(B) E2(A') S(B') ...
+// alternately) through the stages  S (scratch + L1 operand), E1, E2, E3, E4  in strict alternation, B two stages behind A, with
+// E4 of a context's previous tile executed at the head of the S slot of its next tile (see HeadStageSeq below):
+//     ES(A) . E1(A) . E2(A) ES(B) E3(A) E1(B) ES(A') E2(B) E1(A') E3(B) E2(A') ES(B') ...
 // so that between the production of a group's last operand chunk and the read-back of its accumulator the warps always run one
-// stage of the other tile.  Ring, weight slots and the tensor-core warp are shared; the ring order of the chunks follows from the
+// long stage of the other tile.  Ring, weight slots and the tensor-core warp are shared; the ring order of the chunks follows from the
 // same generator (HeadStageSeq) on both sides.  Every (context, group) has its own completion mbarrier (one phase per tile).
 //
 // TMEM columns of context s (base 256 s): acc1 [0,128) L1 pre-activation | acc2 [128,256) L2 pre-activation, then acc3 = dH1
